@@ -1,0 +1,152 @@
+/*
+ * include/nsb.h -- the thin kernel C-ABI ("nsb" = Navier-Stokes B200).
+ *
+ * Plain C, POD arguments, opaque device context, int status (0 = ok, <0 = error;
+ * text via nsb_last_error()). No torch / C++ types cross this boundary. This is
+ * the layer the reference-facing entry points in include/ns_spectral_solver.h are
+ * implemented on (navier-stokes-solvers_b200/csrc/host/spectral_api.c); each call
+ * names the reference function whose work it performs on the device.
+ *
+ * All arrays keep the reference's layouts
+ * (/root/reference/src/spectral/ns_spectral_solver.h:22-68):
+ *   physical  f[j*nx + i]          doubles,          nx*ny
+ *   spectral  f_hat[j*nkx + i]     (re,im) doubles,  nkx*ny with nkx = nx/2+1
+ * nx, ny must be powers of two >= 8.
+ */
+#ifndef NSB_H
+#define NSB_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nsb_ctx nsb_ctx;
+
+typedef struct {
+    int nx, ny;
+    double Lx, Ly, Re;
+    double cfl_factor; /* reference default 0.3 (spectral_memory.c:19) */
+    int device;        /* CUDA device ordinal */
+    /* tuning / test overrides, 0 = automatic */
+    int y1;            /* ny = y1 * Y2 : length of the in-SM column FFT */
+    int x2;            /* nx = X1 * x2 : length of the in-SM row FFT    */
+    int col_tile;      /* columns per column-FFT CTA */
+    int beta_batch;    /* k2 values per beta CTA */
+} nsb_params;
+
+typedef struct {
+    int enabled;              /* cfg.enabled && coefficient > 0 */
+    double coefficient;
+    int order;                /* already clamped to >= 1 */
+    double cutoff_wavenumber; /* derived by ns_spectral_hyperviscosity_update_weights */
+    double inv_bandwidth;
+    int sfd_enabled;          /* cfg.sfd_enabled && sfd_strength > 0 */
+    double sfd_strength;
+    double sfd_timescale;
+} nsb_hyperviscosity;
+
+/* device-resident fields (allocated on first use) */
+enum {
+    NSB_OMEGA_HAT = 0, /* the RK state */
+    NSB_PSI_HAT = 1,
+    NSB_U_HAT = 2,
+    NSB_V_HAT = 3,
+    NSB_NONLINEAR_HAT = 4,
+    NSB_SFD_HAT = 5,
+    NSB_RK_ACC = 6,      /* k1 + 2 k2 + 2 k3 accumulator */
+    NSB_OMEGA_STAGE = 7, /* stage state omega_0 + c dt k */
+    NSB_SCRATCH_HAT = 8,
+    NSB_SCRATCH2_HAT = 9,
+    NSB_NUM_SPECTRAL = 10,
+    NSB_U = 16,
+    NSB_V = 17,
+    NSB_P = 18,
+    NSB_OMEGA = 19,
+    NSB_PSI = 20,
+    NSB_SCRATCH_PHYS = 21,
+    NSB_NUM_FIELDS = 22
+};
+
+const char *nsb_last_error(void);
+int nsb_device_count(void);
+
+/* ns_spectral_allocate + initialize_grids + initialize_fft_plans (spectral_memory.c:6,
+ * spectral_initialization.c:10,57): wavenumber + twiddle tables, work buffers, stream. */
+int nsb_ctx_create(const nsb_params *p, nsb_ctx **out);
+void nsb_ctx_destroy(nsb_ctx *c);
+int nsb_sync(nsb_ctx *c);
+
+/* host <-> device copies of one whole field (reference layout). Synchronous. */
+int nsb_upload(nsb_ctx *c, int field, const void *host);
+int nsb_download(nsb_ctx *c, int field, void *host);
+int nsb_zero(nsb_ctx *c, int field);
+int nsb_copy(nsb_ctx *c, int dst_field, int src_field);
+
+/* ns_spectral_hyperviscosity_set (hyperviscosity.c:32-58): parameters only; weights are
+ * recomputed from (kx,ky) inside the kernels. */
+int nsb_set_hyperviscosity(nsb_ctx *c, const nsb_hyperviscosity *h);
+
+/* Forcing for the NEXT nsb_rk4_step calls (k_s += f_hat, constant over the
+ * step). box[(band+jb)*(ib+1)+i] complex, i in [0,ib], band in [-jb,jb]; copied
+ * asynchronously through a pinned ring. box == NULL disables forcing. */
+int nsb_set_forcing(nsb_ctx *c, int ib, int jb, const double *box);
+
+/* ns_spectral_physical_to_spectral (spectral_transforms.c:9-22): r2c, 1/(nx ny), mask */
+int nsb_physical_to_spectral(nsb_ctx *c, int src_phys, int dst_hat);
+/* ns_spectral_spectral_to_physical (spectral_transforms.c:25-32): mask, c2r; up to 4 fields */
+int nsb_spectral_to_physical(nsb_ctx *c, int nf, const int *src_hat, const int *dst_phys);
+/* ns_spectral_apply_dealiasing (spectral_transforms.c:35-43) */
+int nsb_apply_dealiasing(nsb_ctx *c, int field_hat);
+/* ns_spectral_compute_velocity_from_vorticity (spectral_core.c:8-34) */
+int nsb_velocity_from_vorticity(nsb_ctx *c);
+/* ns_spectral_compute_derivatives (spectral_core.c:37-43): + physical u, v, omega */
+int nsb_compute_derivatives(nsb_ctx *c);
+/* ns_spectral_compute_nonlinear_terms (spectral_core.c:46-112): NONLINEAR_HAT from the
+ * stored PSI_HAT and OMEGA_HAT */
+int nsb_nonlinear_terms(nsb_ctx *c);
+/* ns_spectral_hyperviscosity_apply / _post_step (hyperviscosity.c:104-178) */
+int nsb_hyperviscosity_apply(nsb_ctx *c, int rhs_hat, int state_hat);
+int nsb_hyperviscosity_post_step(nsb_ctx *c, int state_hat, double dt);
+
+/* ns_spectral_compute_cfl_timestep (spectral_time_integration.c:9-31) from the device
+ * copies of the physical u, v arrays. */
+int nsb_cfl_timestep_uv(nsb_ctx *c, double *dt_out);
+/* same, but u, v are formed on the fly from OMEGA_HAT and never stored */
+int nsb_cfl_timestep(nsb_ctx *c, double *dt_out);
+
+/* ns_spectral_advance_rk4 (spectral_time_integration.c:34-106) on OMEGA_HAT, device
+ * resident, asynchronous. dt > 0: use it (data->dt semantics). dt <= 0: the CFL step is
+ * computed on the device from the stage-1 velocity field (the fused max|u| reduction) and
+ * never visits the host. */
+int nsb_rk4_step(nsb_ctx *c, double dt);
+
+/* out[0..2] = sum u^2, sum v^2, sum omega^2 over the grid, out[3] = max(u^2+v^2), from
+ * OMEGA_HAT (ns_spectral_compute_energy/_enstrophy, spectral_analysis.c:8-33, without
+ * materialising the fields). Synchronous. */
+int nsb_diagnostics(nsb_ctx *c, double out[4]);
+/* same sums from the device copies of the physical arrays U, V, OMEGA */
+int nsb_diagnostics_phys(nsb_ctx *c, double out[4]);
+
+/* device-side scalars: last dt, time, number of steps taken. Synchronous. */
+int nsb_get_state(nsb_ctx *c, double *dt, double *t, int *steps);
+int nsb_set_time(nsb_ctx *c, double t);
+/* the last n (<= 256) step sizes, oldest first */
+int nsb_get_dt_history(nsb_ctx *c, int n, double *out);
+
+/* the factorisation in use: out = {Y1, Y2, X1, X2, col_tile, beta_batch, ncol, launches_per_step} */
+int nsb_get_plan(nsb_ctx *c, int out[8]);
+/* cudaStream_t the context launches on (for CUDA-event timing by the caller) */
+void *nsb_stream(nsb_ctx *c);
+/* CUDA-event stopwatch on the context's own stream: start records an event, stop records
+ * a second one, synchronises on it and returns the elapsed device time in ms. */
+int nsb_timer_start(nsb_ctx *c);
+int nsb_timer_stop(nsb_ctx *c, float *ms);
+/* number of kernels this library has launched on this context */
+long long nsb_launch_count(nsb_ctx *c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

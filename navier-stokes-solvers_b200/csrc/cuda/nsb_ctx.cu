@@ -1,0 +1,901 @@
+/*
+ * nsb_ctx.cu -- implementation of include/nsb.h: device context, buffers, kernel
+ * launches. Host-side C++ kept deliberately thin; everything numerical is in
+ * nsb_kernels.cuh / nsb_fft.cuh.
+ */
+#include "nsb_kernels.cuh"
+#include "../../../include/nsb.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <set>
+#include <vector>
+
+#define NSB_MIN_DT 1e-8 /* /root/reference/include/common_types.h:32 */
+#define NSB_MAX_DT 0.1  /* /root/reference/include/common_types.h:33 */
+#define NSB_FORCE_RING 16
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return -1;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define CKL()                                                                              \
+    do {                                                                                   \
+        cudaError_t e_ = cudaGetLastError();                                               \
+        if (e_ != cudaSuccess)                                                             \
+            return fail("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct nsb_ctx {
+    nsb_params prm;
+    NsbGeom g;
+    size_t N, M;
+    int device;
+    cudaStream_t stream;
+    void *fields[NSB_NUM_FIELDS];
+    cd *bufA, *bufB;
+    size_t buf_elems;
+    double *d_kx, *d_ky;
+    cd *d_WY, *d_WX;
+    NsbScalars *d_sc;
+    NsbScalars *h_sc; /* pinned */
+    NsbHv hv;
+    /* forcing */
+    cd *d_force;
+    size_t force_cap;
+    int ib, jb, force_on;
+    cd *h_force[NSB_FORCE_RING];
+    size_t h_force_cap[NSB_FORCE_RING];
+    cudaEvent_t force_ev[NSB_FORCE_RING];
+    int force_slot;
+    int masked_nonzero;
+    int has_beta;
+    long long launches;
+    std::set<const void *> *smem_set;
+    cudaEvent_t ev0, ev1;
+};
+
+extern "C" const char *nsb_last_error(void) { return g_err; }
+
+extern "C" int nsb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+static bool pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+static int field_is_phys(int f) { return f >= NSB_U && f < NSB_NUM_FIELDS; }
+static int field_is_hat(int f) { return f >= 0 && f < NSB_NUM_SPECTRAL; }
+
+static int get_field(nsb_ctx *c, int f, void **out) {
+    if (!field_is_phys(f) && !field_is_hat(f)) return fail("bad field id %d", f);
+    if (!c->fields[f]) {
+        const size_t bytes = field_is_phys(f) ? c->N * sizeof(double) : c->M * sizeof(cd);
+        CK(cudaMalloc(&c->fields[f], bytes));
+        CK(cudaMemsetAsync(c->fields[f], 0, bytes, c->stream));
+    }
+    *out = c->fields[f];
+    return 0;
+}
+
+template <class K>
+static int ensure_smem(nsb_ctx *c, K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return 0;
+    const void *key = (const void *)kernel;
+    if (c->smem_set->count(key)) return 0;
+    if (bytes > 227 * 1024) return fail("kernel needs %zu bytes of shared memory (> 227 KB)", bytes);
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    c->smem_set->insert(key);
+    return 0;
+}
+
+static void fill_twiddles(std::vector<cd> &w, int n) {
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    w.resize(n);
+    for (int k = 0; k < n; ++k) {
+        /* octant reduction keeps the long-double argument small */
+        const int quad = (int)((4LL * k) / n);
+        const int rem = k - (int)(((long long)quad * n) / 4);
+        const long double a = two_pi * (long double)rem / (long double)n;
+        const long double cs = cosl(a), sn = sinl(a);
+        long double re, im;
+        switch (quad) {
+            case 0: re = cs; im = -sn; break;
+            case 1: re = -sn; im = -cs; break;
+            case 2: re = -cs; im = sn; break;
+            default: re = sn; im = cs; break;
+        }
+        w[k] = make_double2((double)re, (double)im);
+    }
+}
+
+extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
+    if (!p || !out) return fail("nsb_ctx_create: null argument");
+    *out = nullptr;
+    if (!pow2(p->nx) || !pow2(p->ny) || p->nx < 8 || p->ny < 8)
+        return fail("nx, ny must be powers of two >= 8 (got %d x %d)", p->nx, p->ny);
+    if (!(p->Lx > 0.0) || !(p->Ly > 0.0) || !(p->Re > 0.0)) return fail("Lx, Ly, Re must be positive");
+#ifndef NSB_EMULATE
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail("no CUDA device visible: this library has no CPU fallback");
+    if (p->device < 0 || p->device >= ndev) return fail("device %d out of range (%d visible)", p->device, ndev);
+#endif
+    CK(cudaSetDevice(p->device));
+    nsb_ctx *c = new nsb_ctx();
+    memset(c->fields, 0, sizeof(c->fields));
+    c->prm = *p;
+    c->device = p->device;
+    c->smem_set = new std::set<const void *>();
+    c->launches = 0;
+    NsbGeom &g = c->g;
+    g.nx = p->nx; g.ny = p->ny; g.nkx = p->nx / 2 + 1;
+    c->N = (size_t)g.nx * g.ny;
+    c->M = (size_t)g.nkx * g.ny;
+    /* factorisation */
+    int Y1 = p->y1 > 0 ? p->y1 : (g.ny <= 1024 ? g.ny : (g.ny / 16 > 1024 ? g.ny / 16 : 1024));
+    int X2 = p->x2 > 0 ? p->x2 : (g.nx <= 1024 ? g.nx : (g.nx / 16 > 1024 ? g.nx / 16 : 1024));
+    if (!pow2(Y1) || Y1 > g.ny || Y1 < 2 || !pow2(X2) || X2 > g.nx || X2 < 2) {
+        delete c->smem_set; delete c;
+        return fail("bad factorisation y1=%d x2=%d", Y1, X2);
+    }
+    g.Y1 = Y1; g.Y2 = g.ny / Y1; g.X2 = X2; g.X1 = g.nx / X2; g.X2h = X2 / 2;
+    if (g.Y2 > 16 || g.X1 > 16) {
+        delete c->smem_set; delete c;
+        return fail("factorisation needs Y2=%d, X1=%d (max 16 each)", g.Y2, g.X1);
+    }
+    g.imax = (2 * g.nkx) / 3;  /* spectral_initialization.c:46 */
+    g.ncol = g.imax + 1;
+    g.ycut = (2 * g.ny) / 6;   /* spectral_initialization.c:48 */
+    g.C = p->col_tile > 0 ? p->col_tile : (4096 / Y1 < 4 ? 4 : (4096 / Y1 > 16 ? 16 : 4096 / Y1));
+    g.BC = p->beta_batch > 0 ? p->beta_batch : 16;
+    const int ncol8 = (g.ncol + 7) & ~7;
+    g.PT = ncol8;
+    g.PH = (g.X1 == 1) ? ncol8 : g.X2h + 2;
+    g.fsT = (size_t)g.ny * g.PT;
+    g.fsH = (size_t)g.ny * g.X1 * g.PH;
+    g.norm = 1.0 / ((double)g.nx * (double)g.ny);
+    c->has_beta = (g.Y2 > 1 || g.X1 > 1);
+    c->buf_elems = 4 * (g.fsT > g.fsH ? g.fsT : g.fsH);
+
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc((void **)&c->bufA, c->buf_elems * sizeof(cd)));
+    CK(cudaMalloc((void **)&c->bufB, c->buf_elems * sizeof(cd)));
+    CK(cudaMemset(c->bufA, 0, c->buf_elems * sizeof(cd)));
+    CK(cudaMemset(c->bufB, 0, c->buf_elems * sizeof(cd)));
+
+    /* wavenumber tables exactly as spectral_initialization.c:25-36 */
+    std::vector<double> kx(g.nkx), ky(g.ny);
+    for (int i = 0; i < g.nkx; ++i) kx[i] = 2.0 * M_PI * i / p->Lx;
+    for (int j = 0; j < g.ny; ++j) ky[j] = (j <= g.ny / 2) ? 2.0 * M_PI * j / p->Ly : 2.0 * M_PI * (j - g.ny) / p->Ly;
+    CK(cudaMalloc((void **)&c->d_kx, kx.size() * sizeof(double)));
+    CK(cudaMalloc((void **)&c->d_ky, ky.size() * sizeof(double)));
+    CK(cudaMemcpy(c->d_kx, kx.data(), kx.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_ky, ky.data(), ky.size() * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<cd> w;
+    fill_twiddles(w, g.ny);
+    CK(cudaMalloc((void **)&c->d_WY, w.size() * sizeof(cd)));
+    CK(cudaMemcpy(c->d_WY, w.data(), w.size() * sizeof(cd), cudaMemcpyHostToDevice));
+    fill_twiddles(w, g.nx);
+    CK(cudaMalloc((void **)&c->d_WX, w.size() * sizeof(cd)));
+    CK(cudaMemcpy(c->d_WX, w.data(), w.size() * sizeof(cd), cudaMemcpyHostToDevice));
+    g.kx = c->d_kx; g.ky = c->d_ky; g.WY = c->d_WY; g.WX = c->d_WX;
+
+    CK(cudaMalloc((void **)&c->d_sc, sizeof(NsbScalars)));
+    CK(cudaMemset(c->d_sc, 0, sizeof(NsbScalars)));
+    CK(cudaMallocHost((void **)&c->h_sc, sizeof(NsbScalars)));
+    memset(c->h_sc, 0, sizeof(NsbScalars));
+    memset(&c->hv, 0, sizeof(c->hv));
+    c->hv.order = 1;
+    c->d_force = nullptr; c->force_cap = 0; c->ib = c->jb = 0; c->force_on = 0; c->force_slot = 0;
+    for (int s = 0; s < NSB_FORCE_RING; ++s) {
+        c->h_force[s] = nullptr; c->h_force_cap[s] = 0;
+        CK(cudaEventCreateWithFlags(&c->force_ev[s], cudaEventDisableTiming));
+    }
+    c->masked_nonzero = 0;
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    void *tmp;
+    if (get_field(c, NSB_OMEGA_HAT, &tmp) || get_field(c, NSB_OMEGA_STAGE, &tmp) || get_field(c, NSB_RK_ACC, &tmp)) {
+        nsb_ctx_destroy(c);
+        return -1;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return 0;
+}
+
+extern "C" void nsb_ctx_destroy(nsb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int f = 0; f < NSB_NUM_FIELDS; ++f) if (c->fields[f]) cudaFree(c->fields[f]);
+    cudaFree(c->bufA); cudaFree(c->bufB);
+    cudaFree(c->d_kx); cudaFree(c->d_ky); cudaFree(c->d_WY); cudaFree(c->d_WX);
+    cudaFree(c->d_sc); cudaFreeHost(c->h_sc);
+    if (c->d_force) cudaFree(c->d_force);
+    for (int s = 0; s < NSB_FORCE_RING; ++s) {
+        if (c->h_force[s]) cudaFreeHost(c->h_force[s]);
+        cudaEventDestroy(c->force_ev[s]);
+    }
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c->smem_set;
+    delete c;
+}
+
+extern "C" int nsb_sync(nsb_ctx *c) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CKL();
+    return 0;
+}
+
+extern "C" int nsb_timer_start(nsb_ctx *c) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    return 0;
+}
+
+extern "C" int nsb_timer_stop(nsb_ctx *c, float *ms) {
+    if (!c || !ms) return fail("nsb_timer_stop: null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    CKL();
+    return 0;
+}
+
+extern "C" void *nsb_stream(nsb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" long long nsb_launch_count(nsb_ctx *c) { return c ? c->launches : 0; }
+
+static int pointwise_grid(nsb_ctx *c) {
+    size_t blocks = (c->M + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    return (int)blocks;
+}
+
+static int scan_masked(nsb_ctx *c) {
+    void *w;
+    if (get_field(c, NSB_OMEGA_HAT, &w)) return -1;
+    CK(cudaMemsetAsync(&c->d_sc->masked_nonzero, 0, sizeof(unsigned), c->stream));
+    auto k = k_scan_masked;
+    NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 0, c->stream, c->g, (const cd *)w, &c->d_sc->masked_nonzero);
+    CKL();
+    c->launches++;
+    unsigned flag = 0;
+    CK(cudaMemcpyAsync(&flag, &c->d_sc->masked_nonzero, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->masked_nonzero = flag ? 1 : 0;
+    return 0;
+}
+
+extern "C" int nsb_upload(nsb_ctx *c, int field, const void *host) {
+    if (!c || !host) return fail("nsb_upload: null argument");
+    CK(cudaSetDevice(c->device));
+    void *d;
+    if (get_field(c, field, &d)) return -1;
+    const size_t bytes = field_is_phys(field) ? c->N * sizeof(double) : c->M * sizeof(cd);
+    CK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (field == NSB_OMEGA_HAT) return scan_masked(c);
+    return 0;
+}
+
+extern "C" int nsb_download(nsb_ctx *c, int field, void *host) {
+    if (!c || !host) return fail("nsb_download: null argument");
+    CK(cudaSetDevice(c->device));
+    void *d;
+    if (get_field(c, field, &d)) return -1;
+    const size_t bytes = field_is_phys(field) ? c->N * sizeof(double) : c->M * sizeof(cd);
+    CK(cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int nsb_zero(nsb_ctx *c, int field) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->device));
+    void *d;
+    if (get_field(c, field, &d)) return -1;
+    const size_t bytes = field_is_phys(field) ? c->N * sizeof(double) : c->M * sizeof(cd);
+    CK(cudaMemsetAsync(d, 0, bytes, c->stream));
+    if (field == NSB_OMEGA_HAT) c->masked_nonzero = 0;
+    return 0;
+}
+
+extern "C" int nsb_copy(nsb_ctx *c, int dst, int src) {
+    if (!c) return fail("null context");
+    if (field_is_phys(dst) != field_is_phys(src)) return fail("nsb_copy: field kinds differ");
+    CK(cudaSetDevice(c->device));
+    void *d, *s;
+    if (get_field(c, dst, &d) || get_field(c, src, &s)) return -1;
+    const size_t bytes = field_is_phys(dst) ? c->N * sizeof(double) : c->M * sizeof(cd);
+    CK(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (dst == NSB_OMEGA_HAT) return scan_masked(c);
+    return 0;
+}
+
+extern "C" int nsb_set_hyperviscosity(nsb_ctx *c, const nsb_hyperviscosity *h) {
+    if (!c || !h) return fail("nsb_set_hyperviscosity: null argument");
+    c->hv.visc = h->enabled ? 1 : 0;
+    c->hv.sfd = h->sfd_enabled ? 1 : 0;
+    c->hv.order = h->order > 0 ? h->order : 1;
+    c->hv.coef = h->coefficient;
+    c->hv.kc = h->cutoff_wavenumber;
+    c->hv.inv_bw = h->inv_bandwidth;
+    c->hv.sfd_strength = h->sfd_strength;
+    c->hv.sfd_timescale = h->sfd_timescale;
+    if (c->hv.sfd) {
+        void *tmp;
+        CK(cudaSetDevice(c->device));
+        if (get_field(c, NSB_SFD_HAT, &tmp)) return -1;
+    }
+    return 0;
+}
+
+extern "C" int nsb_set_forcing(nsb_ctx *c, int ib, int jb, const double *box) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->device));
+    if (!box) { c->force_on = 0; return 0; }
+    if (ib < 0 || jb < 0 || ib > c->g.nx / 2 || jb > c->g.ny / 2) return fail("bad forcing box %d x %d", ib, jb);
+    const size_t elems = (size_t)(2 * jb + 1) * (ib + 1);
+    if (elems > c->force_cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->d_force) CK(cudaFree(c->d_force));
+        CK(cudaMalloc((void **)&c->d_force, elems * sizeof(cd)));
+        c->force_cap = elems;
+    }
+    const int s = c->force_slot;
+    c->force_slot = (s + 1) % NSB_FORCE_RING;
+    CK(cudaEventSynchronize(c->force_ev[s])); /* pinned slot free again? */
+    if (elems > c->h_force_cap[s]) {
+        if (c->h_force[s]) CK(cudaFreeHost(c->h_force[s]));
+        CK(cudaMallocHost((void **)&c->h_force[s], elems * sizeof(cd)));
+        c->h_force_cap[s] = elems;
+    }
+    memcpy(c->h_force[s], box, elems * sizeof(cd));
+    CK(cudaMemcpyAsync(c->d_force, c->h_force[s], elems * sizeof(cd), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->force_ev[s], c->stream));
+    /* modes of the box that the 2/3 mask removes make the masked region live */
+    if (ib > c->g.imax || jb > c->g.ycut) c->masked_nonzero = 1;
+    c->ib = ib; c->jb = jb; c->force_on = 1;
+    return 0;
+}
+
+/* ------------------------------------------------------------ launch helpers */
+
+static int launch_alpha_inv(nsb_ctx *c, int mode, const AlphaInvArgs &a) {
+    const NsbGeom &g = c->g;
+    const dim3 grid((g.ncol + g.C - 1) / g.C, g.Y2), block(256);
+    const size_t smem = (size_t)g.Y1 * g.C * sizeof(cd);
+#define NSB_AI(MODE)                                                     \
+    {                                                                    \
+        auto k = k_alpha_inv<MODE>;                                      \
+        if (ensure_smem(c, k, smem)) return -1;                          \
+        NSB_LAUNCH(k, grid, block, smem, c->stream, g, a);               \
+    }
+    switch (mode) {
+        case NSB_SRC_ARRAYS: NSB_AI(NSB_SRC_ARRAYS); break;
+        case NSB_SRC_STEP: NSB_AI(NSB_SRC_STEP); break;
+        case NSB_SRC_NL: NSB_AI(NSB_SRC_NL); break;
+        default: NSB_AI(NSB_SRC_VEL); break;
+    }
+#undef NSB_AI
+    CKL();
+    c->launches++;
+    return 0;
+}
+
+static int launch_alpha_fwd(nsb_ctx *c, int epi, const AlphaFwdArgs &a) {
+    const NsbGeom &g = c->g;
+    const dim3 grid((g.ncol + g.C - 1) / g.C, g.Y2), block(256);
+    const size_t smem = (size_t)g.Y1 * g.C * sizeof(cd);
+#define NSB_AF(EPI)                                                      \
+    {                                                                    \
+        auto k = k_alpha_fwd<EPI>;                                       \
+        if (ensure_smem(c, k, smem)) return -1;                          \
+        NSB_LAUNCH(k, grid, block, smem, c->stream, g, a);               \
+    }
+    switch (epi) {
+        case NSB_EPI_STORE: NSB_AF(NSB_EPI_STORE); break;
+        case NSB_EPI_NEG: NSB_AF(NSB_EPI_NEG); break;
+        default: NSB_AF(NSB_EPI_RK); break;
+    }
+#undef NSB_AF
+    CKL();
+    c->launches++;
+    return 0;
+}
+
+static size_t beta_smem(const NsbGeom &g) {
+    int nd, nm;
+    nsb_beta_segs(g.imax, g.X1, g.X2, &nd, &nm);
+    return (size_t)g.Y2 * (nd + nm) * g.BC * sizeof(cd);
+}
+
+static int beta_batches(const NsbGeom &g) {
+    const int nk2 = (g.X1 == 1) ? g.ncol : g.X2h + 1;
+    return (nk2 + g.BC - 1) / g.BC;
+}
+
+template <int Y2, int X1>
+static int launch_beta_t(nsb_ctx *c, bool inverse, const BetaArgs &a) {
+    const NsbGeom &g = c->g;
+    const size_t smem = beta_smem(g);
+    const dim3 block(256);
+    if (inverse) {
+        auto k = k_beta_inv<Y2, X1>;
+        if (ensure_smem(c, k, smem)) return -1;
+        NSB_LAUNCH(k, dim3(beta_batches(g), g.Y1, a.nf), block, smem, c->stream, g, a);
+    } else {
+        auto k = k_beta_fwd<Y2, X1>;
+        if (ensure_smem(c, k, smem)) return -1;
+        NSB_LAUNCH(k, dim3(beta_batches(g), g.Y1, 1), block, smem, c->stream, g, a);
+    }
+    CKL();
+    c->launches++;
+    return 0;
+}
+
+template <int Y2>
+static int launch_beta_x(nsb_ctx *c, bool inverse, const BetaArgs &a) {
+    switch (c->g.X1) {
+        case 1: return launch_beta_t<Y2, 1>(c, inverse, a);
+        case 2: return launch_beta_t<Y2, 2>(c, inverse, a);
+        case 4: return launch_beta_t<Y2, 4>(c, inverse, a);
+        case 8: return launch_beta_t<Y2, 8>(c, inverse, a);
+        case 16: return launch_beta_t<Y2, 16>(c, inverse, a);
+    }
+    return fail("unsupported X1=%d", c->g.X1);
+}
+
+static int launch_beta(nsb_ctx *c, bool inverse, const BetaArgs &a) {
+    switch (c->g.Y2) {
+        case 1: return launch_beta_x<1>(c, inverse, a);
+        case 2: return launch_beta_x<2>(c, inverse, a);
+        case 4: return launch_beta_x<4>(c, inverse, a);
+        case 8: return launch_beta_x<8>(c, inverse, a);
+        case 16: return launch_beta_x<16>(c, inverse, a);
+    }
+    return fail("unsupported Y2=%d", c->g.Y2);
+}
+
+static int launch_gamma(nsb_ctx *c, int mode, const GammaArgs &a) {
+    const NsbGeom &g = c->g;
+    const dim3 grid((unsigned)((size_t)g.ny * g.X1 / 2)), block(256);
+    const size_t smem = (size_t)4 * (g.X2 + 1) * sizeof(cd) + 256 * sizeof(double);
+#define NSB_GM(MODE)                                                     \
+    {                                                                    \
+        auto k = k_gamma<MODE>;                                          \
+        if (ensure_smem(c, k, smem)) return -1;                          \
+        NSB_LAUNCH(k, grid, block, smem, c->stream, g, a);               \
+    }
+    switch (mode) {
+        case NSB_GAMMA_STEP: NSB_GM(NSB_GAMMA_STEP); break;
+        case NSB_GAMMA_C2R: NSB_GM(NSB_GAMMA_C2R); break;
+        default: NSB_GM(NSB_GAMMA_R2C); break;
+    }
+#undef NSB_GM
+    CKL();
+    c->launches++;
+    return 0;
+}
+
+/* spectral (masked) -> physical for nf fields produced by alpha source `mode` */
+static int inverse_fields(nsb_ctx *c, int mode, int nf, const cd *const *src, double *const *phys_out,
+                          bool want_umax, bool want_sums) {
+    const NsbGeom &g = c->g;
+    AlphaInvArgs ai;
+    memset(&ai, 0, sizeof(ai));
+    ai.nf = nf;
+    for (int f = 0; f < 4; ++f) ai.src[f] = src[f];
+    ai.out = c->bufA; ai.out_fs = g.fsT; ai.out_pitch = g.PT;
+    if (launch_alpha_inv(c, mode, ai)) return -1;
+    const cd *H = c->bufA;
+    if (c->has_beta) {
+        BetaArgs b; b.in = c->bufA; b.out = c->bufB; b.nf = nf;
+        if (launch_beta(c, true, b)) return -1;
+        H = c->bufB;
+    }
+    GammaArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.in = H;
+    ga.nvalid_in = (g.X1 == 1) ? g.ncol : g.X2h + 1;
+    ga.nf = nf;
+    for (int f = 0; f < 4; ++f) ga.phys_out[f] = (f < nf) ? phys_out[f] : nullptr;
+    ga.umax_bits = want_umax ? &c->d_sc->umax_bits : nullptr;
+    ga.sums = want_sums ? c->d_sc->sums : nullptr;
+    return launch_gamma(c, NSB_GAMMA_C2R, ga);
+}
+
+/* J-bearing H' (in gamma_out) -> spectral, epilogue `epi` */
+static int forward_tail(nsb_ctx *c, const cd *Hp, int epi, AlphaFwdArgs &af) {
+    const NsbGeom &g = c->g;
+    const cd *Tp = Hp;
+    if (c->has_beta) {
+        cd *dst = (Hp == c->bufA) ? c->bufB : c->bufA;
+        BetaArgs b; b.in = Hp; b.out = dst; b.nf = 1;
+        if (launch_beta(c, false, b)) return -1;
+        Tp = dst;
+    }
+    af.in = Tp;
+    af.in_pitch = g.PT;
+    return launch_alpha_fwd(c, epi, af);
+}
+
+/* 4 derivative fields -> Jacobian -> forward, one RK-stage worth of transforms */
+static int nonlinear_pipeline(nsb_ctx *c, int src_mode, const cd *s0, const cd *s1, bool want_umax, int epi,
+                              AlphaFwdArgs &af) {
+    const NsbGeom &g = c->g;
+    AlphaInvArgs ai;
+    memset(&ai, 0, sizeof(ai));
+    ai.nf = 4; ai.src[0] = s0; ai.src[1] = s1;
+    ai.out = c->bufA; ai.out_fs = g.fsT; ai.out_pitch = g.PT;
+    if (launch_alpha_inv(c, src_mode, ai)) return -1;
+    const cd *H = c->bufA;
+    cd *Hp = c->bufB;
+    if (c->has_beta) {
+        BetaArgs b; b.in = c->bufA; b.out = c->bufB; b.nf = 4;
+        if (launch_beta(c, true, b)) return -1;
+        H = c->bufB; Hp = c->bufA;
+    }
+    GammaArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.in = H;
+    ga.nvalid_in = (g.X1 == 1) ? g.ncol : g.X2h + 1;
+    ga.out = Hp;
+    ga.nvalid_out = ga.nvalid_in;
+    ga.nf = 4;
+    ga.umax_bits = want_umax ? &c->d_sc->umax_bits : nullptr;
+    if (launch_gamma(c, NSB_GAMMA_STEP, ga)) return -1;
+    return forward_tail(c, Hp, epi, af);
+}
+
+/* --------------------------------------------------------------- public ops */
+
+extern "C" int nsb_physical_to_spectral(nsb_ctx *c, int src_phys, int dst_hat) {
+    if (!c) return fail("null context");
+    if (!field_is_phys(src_phys) || !field_is_hat(dst_hat)) return fail("nsb_physical_to_spectral: bad fields");
+    CK(cudaSetDevice(c->device));
+    void *src, *dst;
+    if (get_field(c, src_phys, &src) || get_field(c, dst_hat, &dst)) return -1;
+    const NsbGeom &g = c->g;
+    GammaArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.phys_in = (const double *)src;
+    ga.out = c->bufA;
+    ga.nvalid_out = (g.X1 == 1) ? g.ncol : g.X2h + 1;
+    if (launch_gamma(c, NSB_GAMMA_R2C, ga)) return -1;
+    CK(cudaMemsetAsync(dst, 0, c->M * sizeof(cd), c->stream));
+    AlphaFwdArgs af;
+    memset(&af, 0, sizeof(af));
+    af.out = (cd *)dst;
+    if (forward_tail(c, c->bufA, NSB_EPI_STORE, af)) return -1;
+    if (dst_hat == NSB_OMEGA_HAT) c->masked_nonzero = 0;
+    return 0;
+}
+
+extern "C" int nsb_spectral_to_physical(nsb_ctx *c, int nf, const int *src_hat, const int *dst_phys) {
+    if (!c || !src_hat || !dst_phys) return fail("nsb_spectral_to_physical: null argument");
+    if (nf < 1 || nf > 4) return fail("nsb_spectral_to_physical: nf must be 1..4");
+    CK(cudaSetDevice(c->device));
+    const cd *src[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *dst[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int f = 0; f < nf; ++f) {
+        void *s, *d;
+        if (!field_is_hat(src_hat[f]) || !field_is_phys(dst_phys[f])) return fail("nsb_spectral_to_physical: bad fields");
+        if (get_field(c, src_hat[f], &s) || get_field(c, dst_phys[f], &d)) return -1;
+        src[f] = (const cd *)s; dst[f] = (double *)d;
+    }
+    return inverse_fields(c, NSB_SRC_ARRAYS, nf, src, dst, false, false);
+}
+
+extern "C" int nsb_apply_dealiasing(nsb_ctx *c, int field_hat) {
+    if (!c) return fail("null context");
+    if (!field_is_hat(field_hat)) return fail("nsb_apply_dealiasing: bad field");
+    CK(cudaSetDevice(c->device));
+    void *f;
+    if (get_field(c, field_hat, &f)) return -1;
+    auto k = k_apply_dealiasing;
+    NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 0, c->stream, c->g, (cd *)f);
+    CKL();
+    c->launches++;
+    if (field_hat == NSB_OMEGA_HAT) c->masked_nonzero = 0;
+    return 0;
+}
+
+extern "C" int nsb_velocity_from_vorticity(nsb_ctx *c) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->device));
+    void *w, *psi, *uh, *vh;
+    if (get_field(c, NSB_OMEGA_HAT, &w) || get_field(c, NSB_PSI_HAT, &psi) || get_field(c, NSB_U_HAT, &uh) ||
+        get_field(c, NSB_V_HAT, &vh))
+        return -1;
+    auto k = k_velocity_from_vorticity;
+    NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 0, c->stream, c->g, (const cd *)w, (cd *)psi, (cd *)uh, (cd *)vh);
+    CKL();
+    c->launches++;
+    return 0;
+}
+
+extern "C" int nsb_compute_derivatives(nsb_ctx *c) {
+    if (nsb_velocity_from_vorticity(c)) return -1;
+    void *w, *u, *v, *om;
+    if (get_field(c, NSB_OMEGA_HAT, &w) || get_field(c, NSB_U, &u) || get_field(c, NSB_V, &v) ||
+        get_field(c, NSB_OMEGA, &om))
+        return -1;
+    const cd *src[4] = {(const cd *)w, nullptr, nullptr, nullptr};
+    double *dst[4] = {(double *)u, (double *)v, (double *)om, nullptr};
+    return inverse_fields(c, NSB_SRC_VEL, 3, src, dst, false, false);
+}
+
+extern "C" int nsb_nonlinear_terms(nsb_ctx *c) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->device));
+    void *psi, *w, *nl;
+    if (get_field(c, NSB_PSI_HAT, &psi) || get_field(c, NSB_OMEGA_HAT, &w) || get_field(c, NSB_NONLINEAR_HAT, &nl))
+        return -1;
+    CK(cudaMemsetAsync(nl, 0, c->M * sizeof(cd), c->stream));
+    AlphaFwdArgs af;
+    memset(&af, 0, sizeof(af));
+    af.out = (cd *)nl;
+    return nonlinear_pipeline(c, NSB_SRC_NL, (const cd *)psi, (const cd *)w, false, NSB_EPI_NEG, af);
+}
+
+extern "C" int nsb_hyperviscosity_apply(nsb_ctx *c, int rhs_hat, int state_hat) {
+    if (!c) return fail("null context");
+    if (!field_is_hat(rhs_hat) || !field_is_hat(state_hat)) return fail("nsb_hyperviscosity_apply: bad fields");
+    if (!c->hv.visc && !c->hv.sfd) return 0; /* hyperviscosity.c:120-122 */
+    CK(cudaSetDevice(c->device));
+    void *rhs, *st, *sfd = nullptr;
+    if (get_field(c, rhs_hat, &rhs) || get_field(c, state_hat, &st)) return -1;
+    if (c->hv.sfd && get_field(c, NSB_SFD_HAT, &sfd)) return -1;
+    auto k = k_hv_apply;
+    NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 0, c->stream, c->g, c->hv, (cd *)rhs, (const cd *)st, (const cd *)sfd);
+    CKL();
+    c->launches++;
+    return 0;
+}
+
+extern "C" int nsb_hyperviscosity_post_step(nsb_ctx *c, int state_hat, double dt) {
+    if (!c) return fail("null context");
+    if (!field_is_hat(state_hat)) return fail("nsb_hyperviscosity_post_step: bad field");
+    if (!(dt > 0.0) || !c->hv.sfd || !(c->hv.sfd_strength > 0.0) || !(c->hv.sfd_timescale > 0.0)) return 0;
+    CK(cudaSetDevice(c->device));
+    void *st, *sfd;
+    if (get_field(c, state_hat, &st) || get_field(c, NSB_SFD_HAT, &sfd)) return -1;
+    double alpha = dt / c->hv.sfd_timescale;
+    alpha = alpha > 1.0 ? 1.0 : (alpha < 0.0 ? 0.0 : alpha);
+    auto k = k_sfd_post;
+    NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 0, c->stream, c->g, alpha, (cd *)sfd, (const cd *)st);
+    CKL();
+    c->launches++;
+    return 0;
+}
+
+static int launch_cfl(nsb_ctx *c) {
+    const double dx_min = fmin(c->prm.Lx / c->g.nx, c->prm.Ly / c->g.ny);
+    auto k = k_cfl_dt;
+    NSB_LAUNCH(k, dim3(1), dim3(32), 0, c->stream, c->d_sc, c->prm.cfl_factor, dx_min, c->prm.Re, NSB_MIN_DT, NSB_MAX_DT);
+    CKL();
+    c->launches++;
+    return 0;
+}
+
+static int fetch_scalars(nsb_ctx *c) {
+    CK(cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(NsbScalars), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int nsb_cfl_timestep_uv(nsb_ctx *c, double *dt_out) {
+    if (!c || !dt_out) return fail("nsb_cfl_timestep_uv: null argument");
+    CK(cudaSetDevice(c->device));
+    void *u, *v;
+    if (get_field(c, NSB_U, &u) || get_field(c, NSB_V, &v)) return -1;
+    CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
+    size_t blocks = (c->N + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    auto k = k_max_speed2;
+    NSB_LAUNCH(k, dim3((unsigned)blocks), dim3(256), 256 * sizeof(double), c->stream, (const double *)u,
+               (const double *)v, c->N, &c->d_sc->umax_bits);
+    CKL();
+    c->launches++;
+    if (launch_cfl(c) || fetch_scalars(c)) return -1;
+    *dt_out = c->h_sc->dt;
+    return 0;
+}
+
+extern "C" int nsb_cfl_timestep(nsb_ctx *c, double *dt_out) {
+    if (!c || !dt_out) return fail("nsb_cfl_timestep: null argument");
+    CK(cudaSetDevice(c->device));
+    void *w;
+    if (get_field(c, NSB_OMEGA_HAT, &w)) return -1;
+    CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
+    const cd *src[4] = {(const cd *)w, nullptr, nullptr, nullptr};
+    double *dst[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (inverse_fields(c, NSB_SRC_VEL, 2, src, dst, true, false)) return -1;
+    if (launch_cfl(c) || fetch_scalars(c)) return -1;
+    *dt_out = c->h_sc->dt;
+    return 0;
+}
+
+extern "C" int nsb_rk4_step(nsb_ctx *c, double dt) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->device));
+    void *w0, *wst, *acc, *sfd = nullptr;
+    if (get_field(c, NSB_OMEGA_HAT, &w0) || get_field(c, NSB_OMEGA_STAGE, &wst) || get_field(c, NSB_RK_ACC, &acc))
+        return -1;
+    if (c->hv.sfd && get_field(c, NSB_SFD_HAT, &sfd)) return -1;
+    const bool device_dt = !(dt > 0.0);
+    if (!device_dt) {
+        auto k = k_set_dt;
+        NSB_LAUNCH(k, dim3(1), dim3(32), 0, c->stream, c->d_sc, dt);
+        CKL();
+        c->launches++;
+    }
+    for (int stage = 1; stage <= 4; ++stage) {
+        AlphaFwdArgs af;
+        memset(&af, 0, sizeof(af));
+        NsbRk &rk = af.rk;
+        rk.stage = stage;
+        rk.W0 = (cd *)w0; rk.Wst = (cd *)wst; rk.ACC = (cd *)acc; rk.SFD = (cd *)sfd;
+        rk.dt = &c->d_sc->dt;
+        rk.inv_Re = 1.0 / c->prm.Re;
+        rk.hv = c->hv;
+        rk.FB = c->force_on ? c->d_force : nullptr;
+        rk.ib = c->ib; rk.jb = c->jb;
+        const cd *src = (stage == 1) ? (const cd *)w0 : (const cd *)wst;
+        /* the CFL kernel must sit between gamma (stage 1) and the first RK update */
+        const bool want_umax = device_dt && stage == 1;
+        const NsbGeom &g = c->g;
+        AlphaInvArgs ai;
+        memset(&ai, 0, sizeof(ai));
+        ai.nf = 4; ai.src[0] = src;
+        ai.out = c->bufA; ai.out_fs = g.fsT; ai.out_pitch = g.PT;
+        if (launch_alpha_inv(c, NSB_SRC_STEP, ai)) return -1;
+        const cd *H = c->bufA;
+        cd *Hp = c->bufB;
+        if (c->has_beta) {
+            BetaArgs b; b.in = c->bufA; b.out = c->bufB; b.nf = 4;
+            if (launch_beta(c, true, b)) return -1;
+            H = c->bufB; Hp = c->bufA;
+        }
+        GammaArgs ga;
+        memset(&ga, 0, sizeof(ga));
+        ga.in = H;
+        ga.nvalid_in = (g.X1 == 1) ? g.ncol : g.X2h + 1;
+        ga.out = Hp; ga.nvalid_out = ga.nvalid_in; ga.nf = 4;
+        ga.umax_bits = want_umax ? &c->d_sc->umax_bits : nullptr;
+        if (launch_gamma(c, NSB_GAMMA_STEP, ga)) return -1;
+        if (want_umax && launch_cfl(c)) return -1;
+        if (forward_tail(c, Hp, NSB_EPI_RK, af)) return -1;
+        if (c->masked_nonzero) {
+            auto k = k_rk_masked;
+            NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 0, c->stream, g, rk);
+            CKL();
+            c->launches++;
+        }
+    }
+    auto k = k_step_end;
+    NSB_LAUNCH(k, dim3(1), dim3(32), 0, c->stream, c->d_sc);
+    CKL();
+    c->launches++;
+    return 0;
+}
+
+extern "C" int nsb_diagnostics(nsb_ctx *c, double out[4]) {
+    if (!c || !out) return fail("nsb_diagnostics: null argument");
+    CK(cudaSetDevice(c->device));
+    void *w;
+    if (get_field(c, NSB_OMEGA_HAT, &w)) return -1;
+    CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->d_sc->sums, 0, sizeof(double) * 4, c->stream));
+    const cd *src[4] = {(const cd *)w, nullptr, nullptr, nullptr};
+    double *dst[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (inverse_fields(c, NSB_SRC_VEL, 3, src, dst, true, true)) return -1;
+    if (fetch_scalars(c)) return -1;
+    out[0] = c->h_sc->sums[0]; out[1] = c->h_sc->sums[1]; out[2] = c->h_sc->sums[2];
+    double m;
+    memcpy(&m, &c->h_sc->umax_bits, sizeof(double));
+    out[3] = m;
+    CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) k_sumsq3(const double *u, const double *v, const double *w, size_t n,
+                                                NsbScalars *sc) {
+    NSB_DYN_SMEM(double, red);
+    double su = 0.0, sv = 0.0, sw = 0.0, m = 0.0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const double a = u[k], b = v[k], o = w[k];
+        su += a * a; sv += b * b; sw += o * o;
+        m = fmax(m, a * a + b * b);
+    }
+    nsb_block_sum_to_global(su, &sc->sums[0], red);
+    nsb_block_sum_to_global(sv, &sc->sums[1], red);
+    nsb_block_sum_to_global(sw, &sc->sums[2], red);
+    nsb_block_max_to_global(m, &sc->umax_bits, red);
+}
+
+extern "C" int nsb_diagnostics_phys(nsb_ctx *c, double out[4]) {
+    if (!c || !out) return fail("nsb_diagnostics_phys: null argument");
+    CK(cudaSetDevice(c->device));
+    void *u, *v, *w;
+    if (get_field(c, NSB_U, &u) || get_field(c, NSB_V, &v) || get_field(c, NSB_OMEGA, &w)) return -1;
+    CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->d_sc->sums, 0, sizeof(double) * 4, c->stream));
+    size_t blocks = (c->N + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    auto k = k_sumsq3;
+    NSB_LAUNCH(k, dim3((unsigned)blocks), dim3(256), 256 * sizeof(double), c->stream, (const double *)u,
+               (const double *)v, (const double *)w, c->N, c->d_sc);
+    CKL();
+    c->launches++;
+    if (fetch_scalars(c)) return -1;
+    out[0] = c->h_sc->sums[0]; out[1] = c->h_sc->sums[1]; out[2] = c->h_sc->sums[2];
+    double m;
+    memcpy(&m, &c->h_sc->umax_bits, sizeof(double));
+    out[3] = m;
+    CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
+    return 0;
+}
+
+extern "C" int nsb_get_state(nsb_ctx *c, double *dt, double *t, int *steps) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->device));
+    if (fetch_scalars(c)) return -1;
+    if (dt) *dt = c->h_sc->dt;
+    if (t) *t = c->h_sc->t;
+    if (steps) *steps = c->h_sc->step;
+    return 0;
+}
+
+extern "C" int nsb_set_time(nsb_ctx *c, double t) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(&c->d_sc->t, &t, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int nsb_get_dt_history(nsb_ctx *c, int n, double *out) {
+    if (!c || !out) return fail("nsb_get_dt_history: null argument");
+    if (n < 0 || n > 256) return fail("nsb_get_dt_history: n must be 0..256");
+    CK(cudaSetDevice(c->device));
+    if (fetch_scalars(c)) return -1;
+    const int step = c->h_sc->step;
+    if (n > step) return fail("nsb_get_dt_history: only %d steps taken", step);
+    for (int k = 0; k < n; ++k) out[k] = c->h_sc->dt_hist[(step - n + k) & 255];
+    return 0;
+}
+
+extern "C" int nsb_get_plan(nsb_ctx *c, int out[8]) {
+    if (!c || !out) return fail("nsb_get_plan: null argument");
+    const NsbGeom &g = c->g;
+    out[0] = g.Y1; out[1] = g.Y2; out[2] = g.X1; out[3] = g.X2;
+    out[4] = g.C; out[5] = g.BC; out[6] = g.ncol;
+    out[7] = 4 * (c->has_beta ? 5 : 3) + 2;
+    return 0;
+}

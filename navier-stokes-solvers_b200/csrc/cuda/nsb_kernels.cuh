@@ -1,0 +1,716 @@
+/*
+ * nsb_kernels.cuh -- the sm_100a kernels of the pseudospectral RK4 step.
+ *
+ * Replaces, for the hot path of /root/reference/src/spectral:
+ *   spectral_core.c:8-34,46-112       (Poisson solve, ik-derivatives, Jacobian)
+ *   spectral_transforms.c:9-43        (r2c/c2r + 1/(nx ny) + 2/3 mask)
+ *   spectral_time_integration.c:9-106 (CFL dt, RK4 stages, final combine)
+ *   hyperviscosity.c:104-178          (explicit damping, SFD filter)
+ *
+ * 2-D transforms are split as ny = Y1*Y2, nx = X1*X2 ("4-step" in both
+ * directions) so that every on-chip tile fits one SM at any grid size:
+ *
+ *   alpha_inv : spectral pointwise (psi = -w/k^2, i k derivatives, mask) + inverse
+ *               length-Y1 column FFTs + y twiddle            -> T[f][y1][j2][col]
+ *   beta_inv  : length-Y2 DFT over j2, Hermitian gather, length-X1 DFT over k1,
+ *               x twiddle                                     -> H[f][y][x1][k2]
+ *   gamma     : two packed complex length-X2 inverse FFTs per comb (psi_x+i psi_y,
+ *               w_x+i w_y), Jacobian + max|u|^2 in registers/smem, one packed
+ *               forward length-X2 FFT for two combs          -> H'[y][x1][k2]
+ *   beta_fwd  : length-X1 DFT over x1, length-Y2 DFT over y2  -> T'[y1][j2][col]
+ *   alpha_fwd : y twiddle + forward length-Y1 column FFTs + (-1/(nx ny), mask) +
+ *               RHS assembly, damping, forcing, RK stage update in the epilogue.
+ *
+ * When Y2 == X1 == 1 the beta kernels vanish and a stage is three kernels.
+ * Masked columns (kx index > (2 nkx)/3) are never transformed or stored; masked
+ * rows are never loaded. Physical-space fields never touch HBM in the step.
+ */
+#ifndef NSB_KERNELS_CUH
+#define NSB_KERNELS_CUH
+
+#include "nsb_fft.cuh"
+
+struct NsbGeom {
+    int nx, ny, nkx;
+    int Y1, Y2, X1, X2, X2h;
+    int imax, ncol, ycut;
+    int PT, PH;      /* row pitches (complex elements) of the T and H layouts */
+    int C;           /* columns per alpha CTA */
+    int BC;          /* k2 values per beta CTA */
+    size_t fsT, fsH; /* field strides (complex elements) */
+    const double *kx, *ky;
+    const cd *WY, *WX; /* exp(-2 pi i m/ny), exp(-2 pi i m/nx) */
+    double norm;       /* 1/(nx*ny) */
+};
+
+struct NsbHv {
+    int visc, sfd, order;
+    double coef, kc, inv_bw, sfd_strength, sfd_timescale;
+};
+
+struct NsbRk {
+    int stage;
+    cd *W0, *Wst, *ACC, *SFD;
+    const double *dt;
+    double inv_Re;
+    NsbHv hv;
+    const cd *FB; /* forcing box [(band+jb)*(ib+1)+i], nullable */
+    int ib, jb;
+};
+
+__device__ __forceinline__ int nsb_band(int j, int ny) { return (j <= ny / 2) ? j : j - ny; }
+__device__ __forceinline__ int nsb_iabs(int a) { return a < 0 ? -a : a; }
+
+__device__ __forceinline__ double nsb_ipow(double r, int e) {
+    double acc = 1.0, b = r;
+    while (e > 0) {
+        if (e & 1) acc *= b;
+        b *= b;
+        e >>= 1;
+    }
+    return acc;
+}
+
+/* hyperviscosity.c:89-98 : w = c*((|k|-kc)*inv_bw)^order above the cutoff */
+__device__ __forceinline__ double nsb_hv_weight(const NsbHv &h, double kmag) {
+    if (kmag > h.kc) return h.coef * nsb_ipow((kmag - h.kc) * h.inv_bw, h.order);
+    return 0.0;
+}
+
+/* hyperviscosity.c:124-149 : damping = w*state + sfd_strength*ratio^order*(state - sfd) */
+__device__ __forceinline__ cd nsb_damping(const NsbHv &h, double k2, cd W, const cd *SFD, size_t idx) {
+    cd damp = cmk(0.0, 0.0);
+    const double kmag = __dsqrt_rn(k2);
+    if (h.visc) {
+        const double w = nsb_hv_weight(h, kmag);
+        damp.x = __dmul_rn(w, W.x);
+        damp.y = __dmul_rn(w, W.y);
+    }
+    if (h.sfd) {
+        double ratio = 0.0;
+        if (h.inv_bw > 0.0 && kmag > h.kc) {
+            double sc = (kmag - h.kc) * h.inv_bw;
+            sc = sc < 0.0 ? 0.0 : (sc > 1.0 ? 1.0 : sc);
+            ratio = nsb_ipow(sc, h.order);
+        }
+        const double sw = h.sfd_strength * ratio;
+        if (sw > 0.0) {
+            const cd S = SFD[idx];
+            damp.x = __dadd_rn(damp.x, __dmul_rn(sw, __dsub_rn(W.x, S.x)));
+            damp.y = __dadd_rn(damp.y, __dmul_rn(sw, __dsub_rn(W.y, S.y)));
+        }
+    }
+    return damp;
+}
+
+/*
+ * RHS + stage update for one mode. spectral_time_integration.c:50-53 (RHS),
+ * hyperviscosity.c:104-150 (damping), SURVEY 8c (+f), :57-60/:70-73/:83-86 (stage
+ * states), :96-100 (final combine; ACC carries k1+2k2+2k3 in the reference's
+ * summation order), hyperviscosity.c:152-178 (SFD filter update).
+ * Explicit _rn intrinsics keep nvcc from contracting into FMAs so the pointwise
+ * arithmetic rounds like the -ffp-contract=off oracle.
+ */
+__device__ __forceinline__ void nsb_rk_update(const NsbRk &r, size_t idx, double kxv, double kyv, int i,
+                                              int band, cd Nh) {
+    const cd W0v = r.W0[idx];
+    const cd W = (r.stage == 1) ? W0v : r.Wst[idx];
+    const double k2 = __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv));
+    cd k;
+    k.x = __dsub_rn(Nh.x, __dmul_rn(__dmul_rn(k2, W.x), r.inv_Re));
+    k.y = __dsub_rn(Nh.y, __dmul_rn(__dmul_rn(k2, W.y), r.inv_Re));
+    if (r.hv.visc || r.hv.sfd) {
+        const cd damp = nsb_damping(r.hv, k2, W, r.SFD, idx);
+        k.x = __dsub_rn(k.x, damp.x);
+        k.y = __dsub_rn(k.y, damp.y);
+    }
+    if (r.FB != nullptr && i <= r.ib && nsb_iabs(band) <= r.jb) {
+        const cd f = r.FB[(size_t)(band + r.jb) * (r.ib + 1) + i];
+        k.x = __dadd_rn(k.x, f.x);
+        k.y = __dadd_rn(k.y, f.y);
+    }
+    const double dt = *r.dt;
+    if (r.stage == 1) {
+        r.ACC[idx] = k;
+        const double c = __dmul_rn(0.5, dt);
+        r.Wst[idx] = cmk(__dadd_rn(W0v.x, __dmul_rn(c, k.x)), __dadd_rn(W0v.y, __dmul_rn(c, k.y)));
+    } else if (r.stage == 2 || r.stage == 3) {
+        const cd a = r.ACC[idx];
+        r.ACC[idx] = cmk(__dadd_rn(a.x, __dmul_rn(2.0, k.x)), __dadd_rn(a.y, __dmul_rn(2.0, k.y)));
+        const double c = (r.stage == 2) ? __dmul_rn(0.5, dt) : dt;
+        r.Wst[idx] = cmk(__dadd_rn(W0v.x, __dmul_rn(c, k.x)), __dadd_rn(W0v.y, __dmul_rn(c, k.y)));
+    } else {
+        const cd a = r.ACC[idx];
+        const double c = __ddiv_rn(dt, 6.0);
+        const cd Wn = cmk(__dadd_rn(W0v.x, __dmul_rn(c, __dadd_rn(a.x, k.x))),
+                          __dadd_rn(W0v.y, __dmul_rn(c, __dadd_rn(a.y, k.y))));
+        r.W0[idx] = Wn;
+        if (r.hv.sfd && r.hv.sfd_strength > 0.0 && r.hv.sfd_timescale > 0.0 && dt > 0.0) {
+            double al = __ddiv_rn(dt, r.hv.sfd_timescale);
+            al = al > 1.0 ? 1.0 : (al < 0.0 ? 0.0 : al);
+            const cd S = r.SFD[idx];
+            const double om = __dsub_rn(1.0, al);
+            r.SFD[idx] = cmk(__dadd_rn(__dmul_rn(om, S.x), __dmul_rn(al, Wn.x)),
+                             __dadd_rn(__dmul_rn(om, S.y), __dmul_rn(al, Wn.y)));
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ alpha_inv */
+
+enum { NSB_SRC_ARRAYS = 0, NSB_SRC_STEP = 1, NSB_SRC_NL = 2, NSB_SRC_VEL = 3 };
+
+struct AlphaInvArgs {
+    int nf;
+    const cd *src[4];
+    cd *out;
+    size_t out_fs;
+    int out_pitch;
+};
+
+/* spectral_core.c:17-18 : psi = -w/k2, 0 where k2 <= 1e-12 */
+__device__ __forceinline__ cd nsb_psi_from_w(cd W, double k2) {
+    if (k2 > 1e-12) return cmk(__ddiv_rn(-W.x, k2), __ddiv_rn(-W.y, k2));
+    return cmk(0.0, 0.0);
+}
+/* (i k) * z  (spectral_core.c:30-31,66,76,86,96) */
+__device__ __forceinline__ cd nsb_ik(double k, cd z) { return cmk(-(k * z.y), k * z.x); }
+
+template <int MODE>
+__device__ __forceinline__ cd nsb_alpha_source(const NsbGeom &g, const AlphaInvArgs &a, int f, int j, int i) {
+    const size_t idx = (size_t)j * g.nkx + i;
+    if (MODE == NSB_SRC_ARRAYS) return a.src[f][idx];
+    const double kxv = __ldg(&g.kx[i]), kyv = __ldg(&g.ky[j]);
+    if (MODE == NSB_SRC_NL) { /* stored psi_hat (src[0]) and omega_hat (src[1]) */
+        const cd z = (f < 2) ? a.src[0][idx] : a.src[1][idx];
+        return nsb_ik((f & 1) ? kyv : kxv, z);
+    }
+    const cd W = a.src[0][idx];
+    const double k2 = __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv));
+    const cd psi = nsb_psi_from_w(W, k2);
+    if (MODE == NSB_SRC_STEP) {
+        const cd z = (f < 2) ? psi : W;
+        return nsb_ik((f & 1) ? kyv : kxv, z);
+    }
+    /* NSB_SRC_VEL: u_hat = i ky psi, v_hat = -i kx psi, omega_hat */
+    if (f == 0) return nsb_ik(kyv, psi);
+    if (f == 1) { const cd t = nsb_ik(kxv, psi); return cmk(-t.x, -t.y); }
+    return W;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_alpha_inv(NsbGeom g, AlphaInvArgs a) {
+    NSB_DYN_SMEM(cd, s);
+    const int j2 = blockIdx.y;
+    const int ic0 = blockIdx.x * g.C;
+    const int items = g.Y1 * g.C;
+    const int wmul = g.ny / g.Y1;
+    for (int f = 0; f < a.nf; ++f) {
+        for (int w = threadIdx.x; w < items; w += blockDim.x) {
+            const int j1 = w / g.C, c = w - j1 * g.C;
+            const int j = j1 * g.Y2 + j2, ic = ic0 + c;
+            cd v = cmk(0.0, 0.0);
+            if (ic < g.ncol && nsb_iabs(nsb_band(j, g.ny)) <= g.ycut) v = nsb_alpha_source<MODE>(g, a, f, j, ic);
+            s[w] = v;
+        }
+        __syncthreads();
+        nsb_fft_smem_dif<true>(s, g.Y1, g.C, g.C, 1, g.WY, wmul);
+        cd *out = a.out + (size_t)f * a.out_fs;
+        for (int w = threadIdx.x; w < items; w += blockDim.x) {
+            const int p = w / g.C, c = w - p * g.C;
+            const int ic = ic0 + c;
+            if (ic >= g.ncol) continue;
+            const int y1 = nsb_digitrev(p, g.Y1);
+            cd v = s[w];
+            if (g.Y2 > 1) v = cmulc(v, __ldg(&g.WY[(size_t)j2 * y1]));
+            out[(size_t)(y1 * g.Y2 + j2) * a.out_pitch + ic] = v;
+        }
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------ alpha_fwd */
+
+enum { NSB_EPI_STORE = 0, NSB_EPI_NEG = 1, NSB_EPI_RK = 2 };
+
+struct AlphaFwdArgs {
+    const cd *in;
+    int in_pitch;
+    cd *out; /* STORE / NEG: reference-layout spectral array */
+    NsbRk rk;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(256) k_alpha_fwd(NsbGeom g, AlphaFwdArgs a) {
+    NSB_DYN_SMEM(cd, s);
+    const int j2 = blockIdx.y;
+    const int ic0 = blockIdx.x * g.C;
+    const int items = g.Y1 * g.C;
+    const int wmul = g.ny / g.Y1;
+    for (int w = threadIdx.x; w < items; w += blockDim.x) {
+        const int y1 = w / g.C, c = w - y1 * g.C;
+        const int ic = ic0 + c;
+        cd v = cmk(0.0, 0.0);
+        if (ic < g.ncol) {
+            v = a.in[(size_t)(y1 * g.Y2 + j2) * a.in_pitch + ic];
+            if (g.Y2 > 1) v = cmul(v, __ldg(&g.WY[(size_t)j2 * y1]));
+        }
+        s[w] = v;
+    }
+    __syncthreads();
+    nsb_fft_smem_dif<false>(s, g.Y1, g.C, g.C, 1, g.WY, wmul);
+    for (int w = threadIdx.x; w < items; w += blockDim.x) {
+        const int p = w / g.C, c = w - p * g.C;
+        const int ic = ic0 + c;
+        if (ic >= g.ncol) continue;
+        const int j = nsb_digitrev(p, g.Y1) * g.Y2 + j2;
+        const int band = nsb_band(j, g.ny);
+        const bool keep = nsb_iabs(band) <= g.ycut;
+        const size_t idx = (size_t)j * g.nkx + ic;
+        const cd v = s[w];
+        if (EPI == NSB_EPI_STORE) {
+            /* spectral_transforms.c:13-21 : times 1/(nx ny), then mask */
+            a.out[idx] = keep ? cmk(v.x * g.norm, v.y * g.norm) : cmk(0.0, 0.0);
+        } else if (EPI == NSB_EPI_NEG) {
+            /* spectral_core.c:106-111 : nonlinear_hat = -(mask * FFT[J] / (nx ny)) */
+            a.out[idx] = keep ? cmk(-(v.x * g.norm), -(v.y * g.norm)) : cmk(0.0, 0.0);
+        } else {
+            if (!keep) continue; /* masked modes: k_rk_masked, only when they are non-zero */
+            const cd Nh = cmk(-(v.x * g.norm), -(v.y * g.norm));
+            nsb_rk_update(a.rk, idx, __ldg(&g.kx[ic]), __ldg(&g.ky[j]), ic, band, Nh);
+        }
+    }
+}
+
+/* RK update of the modes the 2/3 mask removes (N_hat == 0 there). Linear, so it is
+ * skipped entirely while those modes are all zero (ctx->masked_nonzero == 0). */
+__global__ void __launch_bounds__(256) k_rk_masked(NsbGeom g, NsbRk rk) {
+    const size_t M = (size_t)g.nkx * g.ny;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / g.nkx), i = (int)(idx - (size_t)j * g.nkx);
+        const int band = nsb_band(j, g.ny);
+        if (i <= g.imax && nsb_iabs(band) <= g.ycut) continue;
+        nsb_rk_update(rk, idx, __ldg(&g.kx[i]), __ldg(&g.ky[j]), i, band, cmk(0.0, 0.0));
+    }
+}
+
+/* ----------------------------------------------------------------------- beta */
+
+struct BetaArgs {
+    const cd *in;
+    cd *out;
+    int nf;
+};
+
+/* number of direct (k1) and mirror (k1') column segments that intersect the retained set */
+NSB_HD inline void nsb_beta_segs(int imax, int X1, int X2, int *nd, int *nm) {
+    const int half = (X1 == 1) ? 1 : X1 / 2;
+    int d = imax / X2 + 1;
+    if (d > half) d = half;
+    int m = 0;
+    if (X1 > 1 && imax >= X2 / 2) {
+        m = (imax - X2 / 2) / X2 + 1;
+        if (m > X1 / 2) m = X1 / 2;
+    }
+    *nd = d;
+    *nm = m;
+}
+
+/* column held by segment `seg`, lane cc of batch kb; -1 if outside the retained set */
+__device__ __forceinline__ int nsb_beta_col(const NsbGeom &g, int seg, int nd, int kb, int cc, bool fwd_write) {
+    const int k2 = kb + cc;
+    if (k2 > g.X2h) return -1;
+    int col;
+    if (seg < nd) {
+        col = seg * g.X2 + k2;
+    } else {
+        if (fwd_write && (k2 == 0 || k2 == g.X2h)) return -1; /* duplicates of direct columns */
+        col = (seg - nd) * g.X2 + g.X2 - k2;
+    }
+    return (col <= g.imax) ? col : -1;
+}
+
+/*
+ * beta_inv<Y2,X1>: grid (k2 batches, Y1, nf). For fixed y1:
+ *   step 1  length-Y2 inverse DFT over j2 of T[f][y1][j2][col] for every needed column
+ *   step 2  per (y2,k2): gather k1 = 0..X1-1 (k < nx/2 direct, else conj of column nx-k),
+ *           drop Im of the DC bin (FFTW c2r convention), length-X1 inverse DFT,
+ *           times exp(+2 pi i k2 x1/nx)        -> H[f][y1 + Y1*y2][x1][k2]
+ */
+template <int Y2, int X1>
+__global__ void __launch_bounds__(256) k_beta_inv(NsbGeom g, BetaArgs a) {
+    NSB_DYN_SMEM(cd, tile);
+    const int kb = blockIdx.x * g.BC;
+    const int y1 = blockIdx.y;
+    const int f = blockIdx.z;
+    int nd, nm; /* direct segments k1 = 0..nd-1, mirror segments k1' = 0..nm-1 */
+    nsb_beta_segs(g.imax, X1, g.X2, &nd, &nm);
+    const int nseg = nd + nm;
+    const cd *in = a.in + (size_t)f * g.fsT;
+    cd *out = a.out + (size_t)f * g.fsH;
+    /* step 1 */
+    for (int w = threadIdx.x; w < nseg * g.BC; w += blockDim.x) {
+        const int seg = w / g.BC, cc = w - seg * g.BC;
+        const int col = nsb_beta_col(g, seg, nd, kb, cc, false);
+        cd x[Y2];
+        if (col >= 0) {
+#pragma unroll
+            for (int j2 = 0; j2 < Y2; ++j2) x[j2] = in[(size_t)(y1 * Y2 + j2) * g.PT + col];
+            nsb_dft<Y2, true>(x);
+        } else {
+#pragma unroll
+            for (int j2 = 0; j2 < Y2; ++j2) x[j2] = cmk(0.0, 0.0);
+        }
+#pragma unroll
+        for (int y2 = 0; y2 < Y2; ++y2) tile[(size_t)(y2 * nseg + seg) * g.BC + cc] = x[y2];
+    }
+    __syncthreads();
+    /* step 2 */
+    for (int w = threadIdx.x; w < Y2 * g.BC; w += blockDim.x) {
+        const int y2 = w / g.BC, cc = w - y2 * g.BC;
+        const int k2 = kb + cc;
+        if (k2 > g.X2h) continue;
+        if (X1 == 1 && k2 > g.imax) continue;
+        cd x[X1];
+#pragma unroll
+        for (int k1 = 0; k1 < X1; ++k1) {
+            if (X1 == 1 || k1 < X1 / 2) {
+                x[k1] = (k1 < nd) ? tile[(size_t)(y2 * nseg + k1) * g.BC + cc] : cmk(0.0, 0.0);
+            } else {
+                const int kp = X1 - 1 - k1;
+                x[k1] = (kp < nm) ? cconj(tile[(size_t)(y2 * nseg + nd + kp) * g.BC + cc]) : cmk(0.0, 0.0);
+            }
+        }
+        if (k2 == 0) x[0].y = 0.0;
+        nsb_dft<X1, true>(x);
+        const int y = y1 + g.Y1 * y2;
+#pragma unroll
+        for (int x1 = 0; x1 < X1; ++x1) {
+            cd v = x[x1];
+            if (X1 > 1) v = cmulc(v, __ldg(&g.WX[(size_t)k2 * x1]));
+            out[((size_t)y * X1 + x1) * g.PH + k2] = v;
+        }
+    }
+}
+
+/*
+ * beta_fwd<Y2,X1>: grid (k2 batches, Y1). Mirror of beta_inv for one field:
+ *   step 1  per (y2,k2): H'[y][x1][k2] * exp(-2 pi i k2 x1/nx), length-X1 forward DFT;
+ *           output m is column m*X2+k2, conj(output X1-1-m') is column m'*X2+X2-k2
+ *   step 2  length-Y2 forward DFT over y2              -> T'[y1][j2][col]
+ */
+template <int Y2, int X1>
+__global__ void __launch_bounds__(256) k_beta_fwd(NsbGeom g, BetaArgs a) {
+    NSB_DYN_SMEM(cd, tile);
+    const int kb = blockIdx.x * g.BC;
+    const int y1 = blockIdx.y;
+    int nd, nm;
+    nsb_beta_segs(g.imax, X1, g.X2, &nd, &nm);
+    const int nseg = nd + nm;
+    for (int w = threadIdx.x; w < Y2 * g.BC; w += blockDim.x) {
+        const int y2 = w / g.BC, cc = w - y2 * g.BC;
+        const int k2 = kb + cc;
+        cd x[X1];
+        const bool live = (k2 <= g.X2h) && !(X1 == 1 && k2 > g.imax);
+        if (live) {
+            const int y = y1 + g.Y1 * y2;
+#pragma unroll
+            for (int x1 = 0; x1 < X1; ++x1) {
+                cd v = a.in[((size_t)y * X1 + x1) * g.PH + k2];
+                if (X1 > 1) v = cmul(v, __ldg(&g.WX[(size_t)k2 * x1]));
+                x[x1] = v;
+            }
+            nsb_dft<X1, false>(x);
+        } else {
+#pragma unroll
+            for (int x1 = 0; x1 < X1; ++x1) x[x1] = cmk(0.0, 0.0);
+        }
+#pragma unroll
+        for (int m = 0; m < X1; ++m) {
+            if (X1 == 1 || m < X1 / 2) {
+                if (m < nd) tile[(size_t)(y2 * nseg + m) * g.BC + cc] = x[m];
+            } else {
+                const int kp = X1 - 1 - m;
+                if (kp < nm) tile[(size_t)(y2 * nseg + nd + kp) * g.BC + cc] = cconj(x[m]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < nseg * g.BC; w += blockDim.x) {
+        const int seg = w / g.BC, cc = w - seg * g.BC;
+        const int col = nsb_beta_col(g, seg, nd, kb, cc, true);
+        if (col < 0) continue;
+        cd x[Y2];
+#pragma unroll
+        for (int y2 = 0; y2 < Y2; ++y2) x[y2] = tile[(size_t)(y2 * nseg + seg) * g.BC + cc];
+        nsb_dft<Y2, false>(x);
+#pragma unroll
+        for (int j2 = 0; j2 < Y2; ++j2) a.out[(size_t)(y1 * Y2 + j2) * g.PT + col] = x[j2];
+    }
+}
+
+/* ---------------------------------------------------------------------- gamma */
+
+enum { NSB_GAMMA_STEP = 0, NSB_GAMMA_C2R = 1, NSB_GAMMA_R2C = 2 };
+
+struct GammaArgs {
+    const cd *in;          /* H (STEP: 4 fields, C2R: nf fields) */
+    int nvalid_in;         /* valid k2 entries per comb row of `in` */
+    cd *out;               /* H' (STEP, R2C) */
+    int nvalid_out;
+    int nf;                /* C2R: number of fields (1..4) */
+    double *phys_out[4];   /* C2R: nullable per field */
+    const double *phys_in; /* R2C */
+    unsigned long long *umax_bits; /* nullable: max over points of (f0^2+f1^2) as ordered bits */
+    double *sums;          /* nullable: sums[f] += sum of squares of field f (C2R) */
+};
+
+__device__ __forceinline__ void nsb_block_max_to_global(double v, unsigned long long *dst, double *red) {
+    /* red: blockDim doubles of smem. All threads call. */
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int st = blockDim.x >> 1; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) {
+            const double o = red[threadIdx.x + st];
+            if (o > red[threadIdx.x]) red[threadIdx.x] = o;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicMax(dst, (unsigned long long)__double_as_longlong(red[0]));
+    __syncthreads();
+}
+
+__device__ __forceinline__ void nsb_block_sum_to_global(double v, double *dst, double *red) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int st = blockDim.x >> 1; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(dst, red[0]);
+    __syncthreads();
+}
+
+/*
+ * gamma<MODE>: one CTA per pair of combs (q0 = 2*blockIdx.x, q1 = q0+1), comb q =
+ * (y, x1) = (q / X1, q % X1) holding physical points x = x1 + X1*x2.
+ * smem: 4 sequences of length X2 (pitch SB = X2+1) + blockDim doubles.
+ *   sequence 2*c+pp = packed pair pp (fields 2pp, 2pp+1) of comb c.
+ */
+template <int MODE>
+__global__ void __launch_bounds__(256) k_gamma(NsbGeom g, GammaArgs a) {
+    NSB_DYN_SMEM(cd, s);
+    const int X2 = g.X2, X2h = g.X2h, SB = X2 + 1;
+    double *red = reinterpret_cast<double *>(s + 4 * (size_t)SB);
+    const int q0 = 2 * blockIdx.x;
+    const int wmul = g.nx / X2;
+    const int npair = (MODE == NSB_GAMMA_STEP) ? 2 : (a.nf + 1) / 2;
+    const int nfields = (MODE == NSB_GAMMA_STEP) ? 4 : a.nf;
+
+    if (MODE != NSB_GAMMA_R2C) {
+        /* Hermitian fill: Z[k] = A[k] + i B[k], Z[X2-k] = conj(A[k]) + i conj(B[k]);
+         * Im of the DC and Nyquist bins ignored as FFTW's c2r does. */
+        const int per = X2h + 1;
+        for (int w = threadIdx.x; w < 2 * npair * per; w += blockDim.x) {
+            const int b = w / per, k = w - b * per;
+            const int comb = b / npair, pp = b - comb * npair;
+            const size_t row = (size_t)(q0 + comb) * g.PH;
+            cd A = cmk(0.0, 0.0), B = cmk(0.0, 0.0);
+            if (k < a.nvalid_in) {
+                A = a.in[(size_t)(2 * pp) * g.fsH + row + k];
+                if (2 * pp + 1 < nfields) B = a.in[(size_t)(2 * pp + 1) * g.fsH + row + k];
+            }
+            cd *seq = s + (size_t)(2 * comb + pp) * SB;
+            if (k == 0 || k == X2h) {
+                seq[k] = cmk(A.x, B.x);
+            } else {
+                seq[k] = cmk(A.x - B.y, A.y + B.x);
+                seq[X2 - k] = cmk(A.x + B.y, B.x - A.y);
+            }
+        }
+        __syncthreads();
+        /* sequences used: comb c, pair pp at slot 2c+pp; with npair == 1 slots 0 and 2 */
+        if (npair == 2) {
+            nsb_fft_smem_dif<true>(s, X2, 4, 1, SB, g.WX, wmul);
+        } else {
+            nsb_fft_smem_dif<true>(s, X2, 2, 1, 2 * SB, g.WX, wmul);
+        }
+    }
+
+    if (MODE == NSB_GAMMA_STEP) {
+        double umax = 0.0;
+        for (int p = threadIdx.x; p < X2; p += blockDim.x) {
+            const cd a0 = s[p], b0 = s[SB + p];
+            const cd a1 = s[2 * SB + p], b1 = s[3 * SB + p];
+            /* spectral_core.c:103 : J = psi_x*omega_y - psi_y*omega_x */
+            const double J0 = __dsub_rn(__dmul_rn(a0.x, b0.y), __dmul_rn(a0.y, b0.x));
+            const double J1 = __dsub_rn(__dmul_rn(a1.x, b1.y), __dmul_rn(a1.y, b1.x));
+            /* spectral_time_integration.c:16 : |u|^2 = psi_y^2 + psi_x^2 */
+            const double m0 = __dadd_rn(__dmul_rn(a0.y, a0.y), __dmul_rn(a0.x, a0.x));
+            const double m1 = __dadd_rn(__dmul_rn(a1.y, a1.y), __dmul_rn(a1.x, a1.x));
+            umax = fmax(umax, fmax(m0, m1));
+            s[p] = cmk(J0, J1);
+        }
+        __syncthreads();
+        if (a.umax_bits != nullptr) nsb_block_max_to_global(umax, a.umax_bits, red);
+    } else if (MODE == NSB_GAMMA_C2R) {
+        double umax = 0.0, sq[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = threadIdx.x; w < 2 * X2; w += blockDim.x) {
+            const int comb = w / X2, p = w - comb * X2;
+            const int q = q0 + comb;
+            const int y = q / g.X1, x1 = q - y * g.X1;
+            const size_t o = (size_t)y * g.nx + x1 + (size_t)g.X1 * nsb_digitrev(p, X2);
+            for (int pp = 0; pp < npair; ++pp) {
+                const cd z = s[(size_t)(2 * comb + pp) * SB + p];
+                if (a.phys_out[2 * pp] != nullptr) a.phys_out[2 * pp][o] = z.x;
+                sq[2 * pp] += z.x * z.x;
+                if (2 * pp + 1 < nfields) {
+                    if (a.phys_out[2 * pp + 1] != nullptr) a.phys_out[2 * pp + 1][o] = z.y;
+                    sq[2 * pp + 1] += z.y * z.y;
+                }
+                if (pp == 0) umax = fmax(umax, __dadd_rn(__dmul_rn(z.x, z.x), __dmul_rn(z.y, z.y)));
+            }
+        }
+        __syncthreads();
+        if (a.umax_bits != nullptr) nsb_block_max_to_global(umax, a.umax_bits, red);
+        if (a.sums != nullptr)
+            for (int f = 0; f < nfields; ++f) nsb_block_sum_to_global(sq[f], a.sums + f, red);
+        return;
+    } else { /* R2C: gather the two combs into one packed sequence, digit-reversed */
+        for (int p = threadIdx.x; p < X2; p += blockDim.x) {
+            const int x2 = nsb_digitrev(p, X2);
+            double v[2];
+            for (int comb = 0; comb < 2; ++comb) {
+                const int q = q0 + comb;
+                const int y = q / g.X1, x1 = q - y * g.X1;
+                v[comb] = a.phys_in[(size_t)y * g.nx + x1 + (size_t)g.X1 * x2];
+            }
+            s[p] = cmk(v[0], v[1]);
+        }
+        __syncthreads();
+    }
+
+    /* forward transform of the packed pair (comb0 + i comb1), then split */
+    nsb_fft_smem_dit<false>(s, X2, 1, 1, SB, g.WX, wmul);
+    for (int k = threadIdx.x; k < a.nvalid_out; k += blockDim.x) {
+        const cd P = s[k], Q = s[(X2 - k) & (X2 - 1)];
+        a.out[(size_t)q0 * g.PH + k] = cmk(0.5 * (P.x + Q.x), 0.5 * (P.y - Q.y));
+        a.out[(size_t)(q0 + 1) * g.PH + k] = cmk(0.5 * (P.y + Q.y), -0.5 * (P.x - Q.x));
+    }
+}
+
+/* ------------------------------------------------------------ pointwise kernels */
+
+/* spectral_core.c:8-34 over all modes: psi_hat, u_hat, v_hat from omega_hat */
+__global__ void __launch_bounds__(256) k_velocity_from_vorticity(NsbGeom g, const cd *W, cd *psi, cd *uh, cd *vh) {
+    const size_t M = (size_t)g.nkx * g.ny;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / g.nkx), i = (int)(idx - (size_t)j * g.nkx);
+        const double kxv = g.kx[i], kyv = g.ky[j];
+        const double k2 = __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv));
+        const cd p = nsb_psi_from_w(W[idx], k2);
+        psi[idx] = p;
+        uh[idx] = nsb_ik(kyv, p);
+        const cd t = nsb_ik(kxv, p);
+        vh[idx] = cmk(-t.x, -t.y);
+    }
+}
+
+/* spectral_transforms.c:35-43 */
+__global__ void __launch_bounds__(256) k_apply_dealiasing(NsbGeom g, cd *f) {
+    const size_t M = (size_t)g.nkx * g.ny;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / g.nkx), i = (int)(idx - (size_t)j * g.nkx);
+        if (!(i <= g.imax && nsb_iabs(nsb_band(j, g.ny)) <= g.ycut)) f[idx] = cmk(0.0, 0.0);
+    }
+}
+
+/* flag |= 1 if any mode removed by the mask is non-zero */
+__global__ void __launch_bounds__(256) k_scan_masked(NsbGeom g, const cd *f, unsigned *flag) {
+    const size_t M = (size_t)g.nkx * g.ny;
+    bool hit = false;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / g.nkx), i = (int)(idx - (size_t)j * g.nkx);
+        if (i <= g.imax && nsb_iabs(nsb_band(j, g.ny)) <= g.ycut) continue;
+        const cd v = f[idx];
+        if (v.x != 0.0 || v.y != 0.0) hit = true;
+    }
+    if (hit) atomicOr(flag, 1u);
+}
+
+/* hyperviscosity.c:104-150 as a standalone entry point */
+__global__ void __launch_bounds__(256) k_hv_apply(NsbGeom g, NsbHv hv, cd *rhs, const cd *state, const cd *sfd) {
+    const size_t M = (size_t)g.nkx * g.ny;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / g.nkx), i = (int)(idx - (size_t)j * g.nkx);
+        const double kxv = g.kx[i], kyv = g.ky[j];
+        const double k2 = __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv));
+        const cd d = nsb_damping(hv, k2, state[idx], sfd, idx);
+        const cd r = rhs[idx];
+        rhs[idx] = cmk(__dsub_rn(r.x, d.x), __dsub_rn(r.y, d.y));
+    }
+}
+
+/* hyperviscosity.c:152-178 as a standalone entry point */
+__global__ void __launch_bounds__(256) k_sfd_post(NsbGeom g, double alpha, cd *sfd, const cd *state) {
+    const size_t M = (size_t)g.nkx * g.ny;
+    const double om = 1.0 - alpha;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const cd S = sfd[idx], W = state[idx];
+        sfd[idx] = cmk(__dadd_rn(__dmul_rn(om, S.x), __dmul_rn(alpha, W.x)),
+                       __dadd_rn(__dmul_rn(om, S.y), __dmul_rn(alpha, W.y)));
+    }
+}
+
+/* max over points of u^2+v^2 from physical arrays (EAGER-mode CFL, spectral_time_integration.c:14-20) */
+__global__ void __launch_bounds__(256) k_max_speed2(const double *u, const double *v, size_t n,
+                                                    unsigned long long *umax_bits) {
+    NSB_DYN_SMEM(double, red);
+    double m = 0.0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        m = fmax(m, __dadd_rn(__dmul_rn(u[k], u[k]), __dmul_rn(v[k], v[k])));
+    nsb_block_max_to_global(m, umax_bits, red);
+}
+
+struct NsbScalars {
+    double dt;                     /* time step used by the RK update */
+    double t;                      /* simulation time */
+    unsigned long long umax_bits;  /* max |u|^2 as ordered bits */
+    double sums[4];                /* diagnostic sums of squares */
+    unsigned masked_nonzero;
+    int step;
+    double dt_hist[256];
+};
+
+/* spectral_time_integration.c:22-30 : dt = clamp(min(cfl*dx/(|u|max+1e-12), 0.5*Re*dx^2)) */
+__global__ void k_cfl_dt(NsbScalars *sc, double cfl, double dx_min, double Re, double min_dt, double max_dt) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double max_vel = __dsqrt_rn(__longlong_as_double((long long)sc->umax_bits));
+    const double dt_cfl = __ddiv_rn(__dmul_rn(cfl, dx_min), __dadd_rn(max_vel, 1e-12));
+    const double dt_visc = __dmul_rn(__dmul_rn(__dmul_rn(0.5, Re), dx_min), dx_min);
+    double dt = fmin(dt_cfl, dt_visc);
+    dt = fmax(dt, min_dt);
+    dt = fmin(dt, max_dt);
+    sc->dt = dt;
+    sc->umax_bits = 0ull;
+}
+
+__global__ void k_set_dt(NsbScalars *sc, double dt) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) sc->dt = dt;
+}
+
+/* spectral_time_integration.c:104 : t += dt (plus a small dt history ring for the host) */
+__global__ void k_step_end(NsbScalars *sc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    sc->t = __dadd_rn(sc->t, sc->dt);
+    sc->dt_hist[sc->step & 255] = sc->dt;
+    sc->step += 1;
+}
+
+#endif

@@ -1,0 +1,52 @@
+"""Kernel-logic tests that run WITHOUT a GPU: the product's .cu sources compiled for the
+CPU emulator (tests/emu) checked against the CPU oracle at small sizes, including
+factorisations that mimic the 16384^2 plan (Y2 = X1 = 16) in miniature."""
+import pytest
+
+import parity_cases as pc
+from conftest import best_oracle_kind
+
+HV = dict(enabled=1, coefficient=0.5, order=4, cutoff_ratio=0.3)
+SFD = dict(enabled=1, coefficient=0.5, order=4, cutoff_ratio=0.3, sfd_enabled=1, sfd_strength=0.3,
+           sfd_timescale=0.4)
+
+PLANS = [
+    (32, 32, {}),
+    (64, 32, dict(y1=8, x2=8)),
+    (64, 64, dict(y1=16, x2=32)),
+    (128, 64, dict(y1=4, x2=8, col_tile=4, beta_batch=4)),
+    (64, 128, dict(y1=128, x2=4)),
+]
+
+
+@pytest.mark.parametrize("nx,ny,plan", PLANS)
+def test_emu_transforms(nsb, emu_lib, oracles, nx, ny, plan):
+    pc.check_transforms(nsb, emu_lib, oracles, best_oracle_kind(oracles), nx, ny, **plan)
+
+
+@pytest.mark.parametrize("nx,ny,plan", PLANS[:3])
+def test_emu_operators(nsb, emu_lib, oracles, nx, ny, plan):
+    pc.check_operators(nsb, emu_lib, oracles, best_oracle_kind(oracles), nx, ny, **plan)
+
+
+def test_emu_step_plain(nsb, emu_lib, oracles):
+    pc.check_per_step(nsb, emu_lib, oracles, best_oracle_kind(oracles), 32, 32, 3)
+
+
+def test_emu_step_taylor_green_host_dt(nsb, emu_lib, oracles):
+    pc.check_per_step(nsb, emu_lib, oracles, best_oracle_kind(oracles), 32, 32, 2, init="tg", Re=100.0,
+                      device_dt=False)
+
+
+def test_emu_step_forced_white_split(nsb, emu_lib, oracles):
+    pc.check_per_step(nsb, emu_lib, oracles, best_oracle_kind(oracles), 64, 32, 2, hv=HV,
+                      forcing=dict(kind="white"), y1=8, x2=16)
+
+
+def test_emu_step_forced_colored_sfd_split(nsb, emu_lib, oracles):
+    pc.check_per_step(nsb, emu_lib, oracles, best_oracle_kind(oracles), 32, 64, 2, hv=SFD,
+                      forcing=dict(kind="colored"), y1=16, x2=8, col_tile=4, beta_batch=4)
+
+
+def test_emu_free_running(nsb, emu_lib, oracles):
+    pc.check_free_running(nsb, emu_lib, oracles, best_oracle_kind(oracles), 32, 32, 20, every=5, hv=HV)

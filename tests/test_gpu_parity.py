@@ -1,0 +1,93 @@
+"""Parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from conftest import best_oracle_kind
+
+pytestmark = pytest.mark.gpu
+
+HV = dict(enabled=1, coefficient=5.0, order=4, cutoff_ratio=0.3)
+SFD = dict(enabled=1, coefficient=0.5, order=4, cutoff_ratio=0.3, sfd_enabled=1, sfd_strength=0.3,
+           sfd_timescale=0.4)
+
+
+@pytest.mark.parametrize("nx,ny,plan", [
+    (32, 32, {}), (64, 32, dict(y1=8, x2=8)), (128, 64, dict(y1=4, x2=8, col_tile=4, beta_batch=4)),
+    (256, 256, {}), (512, 256, dict(y1=64, x2=128)), (2048, 2048, {}),
+])
+def test_transforms(nsb, cuda_lib, oracles, nx, ny, plan):
+    pc.check_transforms(nsb, cuda_lib, oracles, best_oracle_kind(oracles), nx, ny, **plan)
+
+
+@pytest.mark.parametrize("nx,ny,plan", [(64, 64, {}), (128, 128, dict(y1=16, x2=32)), (1024, 1024, {})])
+def test_operators(nsb, cuda_lib, oracles, nx, ny, plan):
+    pc.check_operators(nsb, cuda_lib, oracles, best_oracle_kind(oracles), nx, ny, **plan)
+
+
+def test_step_taylor_green_128(nsb, cuda_lib, oracles):
+    """BASELINE config 1: TG 128^2, nu = 0.01, adaptive dt."""
+    pc.check_per_step(nsb, cuda_lib, oracles, best_oracle_kind(oracles), 128, 128, 10, init="tg", Re=100.0)
+
+
+def test_step_decaying_1024(nsb, cuda_lib, oracles):
+    """BASELINE config 2: decaying 1024^2 random-phase, hyperviscosity."""
+    pc.check_per_step(nsb, cuda_lib, oracles, best_oracle_kind(oracles), 1024, 1024, 3, hv=HV, Re=1e4)
+
+
+def test_step_forced_white_split_plan(nsb, cuda_lib, oracles):
+    """the 16384^2 plan (Y2 = X1 = 16) in miniature, forced"""
+    pc.check_per_step(nsb, cuda_lib, oracles, best_oracle_kind(oracles), 512, 512, 3, hv=HV,
+                      forcing=dict(kind="white"), Re=1e4, y1=32, x2=32)
+
+
+def test_step_forced_colored_sfd(nsb, cuda_lib, oracles):
+    pc.check_per_step(nsb, cuda_lib, oracles, best_oracle_kind(oracles), 256, 128, 4, hv=SFD,
+                      forcing=dict(kind="colored"), y1=32, x2=64)
+
+
+def test_step_forced_4096_few_steps(nsb, cuda_lib, oracles):
+    """BASELINE config 3 at full size, 2 steps (the oracle needs ~2.3 GB and ~1 min)."""
+    pc.check_per_step(nsb, cuda_lib, oracles, best_oracle_kind(oracles), 4096, 4096, 2, hv=HV,
+                      forcing=dict(kind="white"), Re=1e4)
+
+
+def test_free_running_1000_steps_128(nsb, cuda_lib, oracles):
+    """north-star: E and enstrophy within 1e-9 relative over 1000 free-running steps."""
+    pc.check_free_running(nsb, cuda_lib, oracles, best_oracle_kind(oracles), 128, 128, 1000, every=10,
+                          hv=dict(enabled=1, coefficient=0.5, order=4, cutoff_ratio=0.3))
+
+
+def test_free_running_forced_256(nsb, cuda_lib, oracles):
+    pc.check_free_running(nsb, cuda_lib, oracles, best_oracle_kind(oracles), 256, 256, 200, every=10, hv=HV,
+                          forcing=dict(kind="white"), Re=1e4)
+
+
+def test_large_size_properties_16384(nsb, cuda_lib):
+    """Size-independent properties at the full 16384^2 size (no oracle: 37 GB on the CPU):
+    r2c(c2r(w)) == w on the retained set, masked modes zero, Taylor-Green energy decay."""
+    n = 16384
+    c = nsb.NsbContext(n, n, Re=100.0, lib=cuda_lib)
+    rng = np.random.default_rng(3)
+    nkx = n // 2 + 1
+    w = np.zeros((n, nkx), dtype=np.complex128)
+    kk = 64
+    blk = rng.standard_normal((2 * kk + 1, kk + 1)) + 1j * rng.standard_normal((2 * kk + 1, kk + 1))
+    rows = np.arange(-kk, kk + 1) % n
+    w[rows[:, None], np.arange(kk + 1)[None, :]] = blk
+    w[0, 0] = 0.0
+    # Hermitian-project the kx = 0 column so the field is the spectrum of a real field
+    col = w[:, 0].copy()
+    w[:, 0] = 0.5 * (col + np.conj(col[(-np.arange(n)) % n]))
+    c.upload(nsb.OMEGA_HAT, w)
+    c.spectral_to_physical([nsb.OMEGA_HAT], [nsb.OMEGA])
+    c.physical_to_spectral(nsb.OMEGA, nsb.SCRATCH_HAT)
+    back = c.download(nsb.SCRATCH_HAT)
+    assert pc.rel(back, w) < 1e-13
+    d0 = c.diagnostics()
+    for _ in range(2):
+        c.step(0.0)
+    d1 = c.diagnostics()
+    assert 0 < d1["energy"] < d0["energy"]
+    assert 0 < d1["enstrophy"] < d0["enstrophy"]
+    c.close()
