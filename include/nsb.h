@@ -143,6 +143,12 @@ void *nsb_stream(nsb_ctx *c);
  * a second one, synchronises on it and returns the elapsed device time in ms. */
 int nsb_timer_start(nsb_ctx *c);
 int nsb_timer_stop(nsb_ctx *c, float *ms);
+/* Per-kernel device timing with CUDA events on the context's stream, for the roofline
+ * numbers bench.py reports. Between begin and end every transform kernel launch is
+ * bracketed by two events; end returns the summed ms and launch counts per kind:
+ * 0 alpha_inv, 1 beta_inv, 2 gamma, 3 beta_fwd, 4 alpha_fwd, 5 other. */
+int nsb_profile_begin(nsb_ctx *c);
+int nsb_profile_end(nsb_ctx *c, double ms[6], int count[6]);
 /* number of kernels this library has launched on this context */
 long long nsb_launch_count(nsb_ctx *c);
 

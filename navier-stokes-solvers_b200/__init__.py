@@ -52,7 +52,7 @@ def load_nsb(path=None):
     if not os.path.exists(path):
         raise NsbError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
                        " (nvcc, sm_100a). There is no CPU fallback.")
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path)
     lib.nsb_last_error.restype = C.c_char_p
     lib.nsb_ctx_create.argtypes = [C.POINTER(NsbParams), C.POINTER(C.c_void_p)]
     lib.nsb_ctx_destroy.argtypes = [C.c_void_p]
@@ -86,6 +86,8 @@ def load_nsb(path=None):
         "nsb_set_time": [C.c_void_p, C.c_double],
         "nsb_get_dt_history": [C.c_void_p, C.c_int, c_double_p],
         "nsb_get_plan": [C.c_void_p, C.POINTER(C.c_int)],
+        "nsb_profile_begin": [C.c_void_p],
+        "nsb_profile_end": [C.c_void_p, c_double_p, C.POINTER(C.c_int)],
         "nsb_timer_start": [C.c_void_p],
         "nsb_timer_stop": [C.c_void_p, C.POINTER(C.c_float)],
     }

@@ -69,7 +69,28 @@ struct nsb_ctx {
     long long launches;
     std::set<const void *> *smem_set;
     cudaEvent_t ev0, ev1;
+    /* optional per-kernel CUDA-event timing (nsb_profile_begin/_end) */
+    int prof_on;
+    std::vector<cudaEvent_t> *prof_ev; /* pairs */
+    std::vector<int> *prof_kind;
 };
+
+enum { PK_ALPHA_INV = 0, PK_BETA_INV, PK_GAMMA, PK_BETA_FWD, PK_ALPHA_FWD, PK_OTHER, PK_COUNT };
+
+static void prof_pre(nsb_ctx *c, int kind) {
+    if (!c->prof_on) return;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    c->prof_ev->push_back(e0);
+    c->prof_ev->push_back(e1);
+    c->prof_kind->push_back(kind);
+    cudaEventRecord(e0, c->stream);
+}
+static void prof_post(nsb_ctx *c) {
+    if (!c->prof_on) return;
+    cudaEventRecord(c->prof_ev->back(), c->stream);
+}
 
 extern "C" const char *nsb_last_error(void) { return g_err; }
 
@@ -145,6 +166,9 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->device = p->device;
     c->smem_set = new std::set<const void *>();
     c->launches = 0;
+    c->prof_on = 0;
+    c->prof_ev = new std::vector<cudaEvent_t>();
+    c->prof_kind = new std::vector<int>();
     NsbGeom &g = c->g;
     g.nx = p->nx; g.ny = p->ny; g.nkx = p->nx / 2 + 1;
     c->N = (size_t)g.nx * g.ny;
@@ -237,8 +261,37 @@ extern "C" void nsb_ctx_destroy(nsb_ctx *c) {
     }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
+    for (cudaEvent_t e : *c->prof_ev) cudaEventDestroy(e);
+    delete c->prof_ev;
+    delete c->prof_kind;
     delete c->smem_set;
     delete c;
+}
+
+extern "C" int nsb_profile_begin(nsb_ctx *c) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (cudaEvent_t e : *c->prof_ev) cudaEventDestroy(e);
+    c->prof_ev->clear();
+    c->prof_kind->clear();
+    c->prof_on = 1;
+    return 0;
+}
+
+extern "C" int nsb_profile_end(nsb_ctx *c, double ms[6], int count[6]) {
+    if (!c || !ms || !count) return fail("nsb_profile_end: null argument");
+    CK(cudaSetDevice(c->device));
+    c->prof_on = 0;
+    CK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < PK_COUNT; ++k) { ms[k] = 0.0; count[k] = 0; }
+    for (size_t k = 0; k < c->prof_kind->size(); ++k) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, (*c->prof_ev)[2 * k], (*c->prof_ev)[2 * k + 1]));
+        ms[(*c->prof_kind)[k]] += t;
+        count[(*c->prof_kind)[k]] += 1;
+    }
+    return 0;
 }
 
 extern "C" int nsb_sync(nsb_ctx *c) {
@@ -395,6 +448,7 @@ static int launch_alpha_inv(nsb_ctx *c, int mode, const AlphaInvArgs &a) {
         if (ensure_smem(c, k, smem)) return -1;                          \
         NSB_LAUNCH(k, grid, block, smem, c->stream, g, a);               \
     }
+    prof_pre(c, PK_ALPHA_INV);
     switch (mode) {
         case NSB_SRC_ARRAYS: NSB_AI(NSB_SRC_ARRAYS); break;
         case NSB_SRC_STEP: NSB_AI(NSB_SRC_STEP); break;
@@ -402,6 +456,7 @@ static int launch_alpha_inv(nsb_ctx *c, int mode, const AlphaInvArgs &a) {
         default: NSB_AI(NSB_SRC_VEL); break;
     }
 #undef NSB_AI
+    prof_post(c);
     CKL();
     c->launches++;
     return 0;
@@ -417,12 +472,14 @@ static int launch_alpha_fwd(nsb_ctx *c, int epi, const AlphaFwdArgs &a) {
         if (ensure_smem(c, k, smem)) return -1;                          \
         NSB_LAUNCH(k, grid, block, smem, c->stream, g, a);               \
     }
+    prof_pre(c, PK_ALPHA_FWD);
     switch (epi) {
         case NSB_EPI_STORE: NSB_AF(NSB_EPI_STORE); break;
         case NSB_EPI_NEG: NSB_AF(NSB_EPI_NEG); break;
         default: NSB_AF(NSB_EPI_RK); break;
     }
 #undef NSB_AF
+    prof_post(c);
     CKL();
     c->launches++;
     return 0;
@@ -444,6 +501,7 @@ static int launch_beta_t(nsb_ctx *c, bool inverse, const BetaArgs &a) {
     const NsbGeom &g = c->g;
     const size_t smem = beta_smem(g);
     const dim3 block(256);
+    prof_pre(c, inverse ? PK_BETA_INV : PK_BETA_FWD);
     if (inverse) {
         auto k = k_beta_inv<Y2, X1>;
         if (ensure_smem(c, k, smem)) return -1;
@@ -453,6 +511,7 @@ static int launch_beta_t(nsb_ctx *c, bool inverse, const BetaArgs &a) {
         if (ensure_smem(c, k, smem)) return -1;
         NSB_LAUNCH(k, dim3(beta_batches(g), g.Y1, 1), block, smem, c->stream, g, a);
     }
+    prof_post(c);
     CKL();
     c->launches++;
     return 0;
@@ -491,12 +550,14 @@ static int launch_gamma(nsb_ctx *c, int mode, const GammaArgs &a) {
         if (ensure_smem(c, k, smem)) return -1;                          \
         NSB_LAUNCH(k, grid, block, smem, c->stream, g, a);               \
     }
+    prof_pre(c, PK_GAMMA);
     switch (mode) {
         case NSB_GAMMA_STEP: NSB_GM(NSB_GAMMA_STEP); break;
         case NSB_GAMMA_C2R: NSB_GM(NSB_GAMMA_C2R); break;
         default: NSB_GM(NSB_GAMMA_R2C); break;
     }
 #undef NSB_GM
+    prof_post(c);
     CKL();
     c->launches++;
     return 0;

@@ -1,0 +1,234 @@
+/*
+ * main_spectral.c -- the ns_spectral_solver CLI on the B200 backend.
+ *
+ * Same run shape and console lines as /root/reference/src/spectral/main_spectral.c
+ * (allocate -> grids -> plans -> initial condition -> while (t < t_end) { dt = cfl;
+ * advance_rk4; diagnostics every 10, resolution check every 100, dump every
+ * output.interval }), but
+ *   - it takes the `--config <file>` arguments the reference README documents
+ *     (README.md:67-77) and actually reads them through ns_config (the reference
+ *     binary ignores argv);
+ *   - the time loop is device resident (NS_SYNC_LAZY + ns_spectral_run_steps).
+ *
+ * Keys (defaults in brackets):
+ *   solver.type [spectral]   grid.nx grid.ny [128]   domain.Lx domain.Ly [2*pi]
+ *   fluid.Re [1000]  time.t_end [5]  time.max_steps [0 = unlimited]  time.cfl [0.3]
+ *   forcing.type none|white|colored [none]  forcing.energy_target [1]
+ *   forcing.correlation_time [0.5]  forcing.seed [0]  forcing.kmin [0]  forcing.kmax [4]
+ *   spectral.hyperviscosity.coefficient [0 = off]  .order [8]  .cutoff_ratio [0.65]
+ *   spectral.sfd.strength [0 = off]  spectral.sfd.timescale [1]
+ *   init.type taylor_green|random_phase [taylor_green]  init.seed [7]  init.k0 [8]
+ *   init.max_omega [5]   output.interval [50, 0 = none]  output.prefix [spectral_solution]
+ *   backend.device [0]
+ */
+#include "ns_config.h"
+#include "ns_spectral_solver.h"
+
+#include <time.h>
+
+static double now_seconds(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static int load_config(int argc, char **argv, NSConfig *cfg) {
+    const char *paths[64];
+    size_t n = 0;
+    for (int a = 1; a < argc; ++a) {
+        if (strcmp(argv[a], "--config") == 0 && a + 1 < argc) {
+            if (n < 64) paths[n++] = argv[++a];
+        } else if (strcmp(argv[a], "--help") == 0 || strcmp(argv[a], "-h") == 0) {
+            printf("usage: ns_spectral_solver [--config file.ini|file.json]...\n");
+            return 1;
+        } else {
+            fprintf(stderr, "unknown argument: %s\n", argv[a]);
+            return -1;
+        }
+    }
+    char err[256] = "";
+    if (ns_config_load_files(cfg, paths, n, err, sizeof err) != 0) {
+        fprintf(stderr, "configuration error: %s\n", err);
+        return -1;
+    }
+    static const char *solver_ok[] = {"spectral", "finite_difference"};
+    static const char *forcing_ok[] = {"none", "white", "colored"};
+    static const char *init_ok[] = {"taylor_green", "random_phase"};
+    const NSConfigSchemaEntry schema[] = {
+        {"solver.type", NS_CONFIG_VALUE_STRING, 0, 0, 0, 0, 0, solver_ok, 2},
+        {"grid.nx", NS_CONFIG_VALUE_INT, 0, 8, 0, 1, 0, NULL, 0},
+        {"grid.ny", NS_CONFIG_VALUE_INT, 0, 8, 0, 1, 0, NULL, 0},
+        {"domain.Lx", NS_CONFIG_VALUE_DOUBLE, 0, 1e-6, 0, 1, 0, NULL, 0},
+        {"domain.Ly", NS_CONFIG_VALUE_DOUBLE, 0, 1e-6, 0, 1, 0, NULL, 0},
+        {"fluid.Re", NS_CONFIG_VALUE_DOUBLE, 0, 1e-6, 0, 1, 0, NULL, 0},
+        {"time.dt", NS_CONFIG_VALUE_DOUBLE, 0, 1e-9, 0, 1, 0, NULL, 0},
+        {"time.t_end", NS_CONFIG_VALUE_DOUBLE, 0, 1e-9, 0, 1, 0, NULL, 0},
+        {"time.max_steps", NS_CONFIG_VALUE_INT, 0, 0, 0, 1, 0, NULL, 0},
+        {"time.cfl", NS_CONFIG_VALUE_DOUBLE, 0, 1e-6, 0, 1, 0, NULL, 0},
+        {"forcing.type", NS_CONFIG_VALUE_STRING, 0, 0, 0, 0, 0, forcing_ok, 3},
+        {"forcing.energy_target", NS_CONFIG_VALUE_DOUBLE, 0, 0, 0, 1, 0, NULL, 0},
+        {"forcing.correlation_time", NS_CONFIG_VALUE_DOUBLE, 0, 0, 0, 1, 0, NULL, 0},
+        {"spectral.hyperviscosity.coefficient", NS_CONFIG_VALUE_DOUBLE, 0, 0, 0, 1, 0, NULL, 0},
+        {"spectral.hyperviscosity.order", NS_CONFIG_VALUE_INT, 0, 0, 0, 1, 0, NULL, 0},
+        {"spectral.hyperviscosity.cutoff_ratio", NS_CONFIG_VALUE_DOUBLE, 0, 0, 1, 1, 1, NULL, 0},
+        {"init.type", NS_CONFIG_VALUE_STRING, 0, 0, 0, 0, 0, init_ok, 2},
+        {"output.interval", NS_CONFIG_VALUE_INT, 0, 0, 0, 1, 0, NULL, 0},
+        {"backend.device", NS_CONFIG_VALUE_INT, 0, 0, 0, 1, 0, NULL, 0},
+    };
+    if (ns_config_validate(cfg, schema, sizeof schema / sizeof schema[0], err, sizeof err) != 0) {
+        fprintf(stderr, "configuration error: %s\n", err);
+        return -1;
+    }
+    return 0;
+}
+
+int main(int argc, char *argv[]) {
+    NSConfig cfg;
+    ns_config_init(&cfg);
+    const int rc = load_config(argc, argv, &cfg);
+    if (rc != 0) {
+        ns_config_free(&cfg);
+        return rc < 0 ? 2 : 0;
+    }
+    if (strcmp(ns_config_get_string(&cfg, "solver.type", "spectral"), "spectral") != 0) {
+        fprintf(stderr, "solver.type = %s: only the spectral solver is built here\n",
+                ns_config_get_string(&cfg, "solver.type", ""));
+        ns_config_free(&cfg);
+        return 2;
+    }
+
+    printf("Spectral Navier-Stokes Solver\n");
+    printf("Fourier Methods with RK4 Time Integration\n\n");
+
+    const int nx = ns_config_get_int(&cfg, "grid.nx", 128), ny = ns_config_get_int(&cfg, "grid.ny", 128);
+    const double Lx = ns_config_get_double(&cfg, "domain.Lx", 2 * M_PI);
+    const double Ly = ns_config_get_double(&cfg, "domain.Ly", 2 * M_PI);
+    const double Re = ns_config_get_double(&cfg, "fluid.Re", 1000.0);
+    const double t_final = ns_config_get_double(&cfg, "time.t_end", 5.0);
+    const int max_steps = ns_config_get_int(&cfg, "time.max_steps", 0);
+    const int output_interval = ns_config_get_int(&cfg, "output.interval", 50);
+    const char *prefix = ns_config_get_string(&cfg, "output.prefix", "spectral_solution");
+
+    printf("Resolution: %dx%d modes\n", nx, ny);
+    printf("Domain: [0,%.2f] x [0,%.2f]\n", Lx, Ly);
+    printf("Reynolds number: %.1f\n\n", Re);
+
+    NSSpectralData *data = ns_spectral_allocate(nx, ny, Lx, Ly, Re);
+    if (!data) {
+        printf("Memory allocation failed!\n");
+        return 1;
+    }
+    data->cfl_factor = ns_config_get_double(&cfg, "time.cfl", 0.3);
+    ns_spectral_backend_select_device(data, ns_config_get_int(&cfg, "backend.device", 0));
+    ns_spectral_initialize_grids(data);
+    ns_spectral_initialize_fft_plans(data);
+    if (!data->forward_plan) {
+        fprintf(stderr, "no usable CUDA device: %s\n", ns_spectral_last_error());
+        ns_spectral_free(data);
+        return 3;
+    }
+
+    if (strcmp(ns_config_get_string(&cfg, "init.type", "taylor_green"), "random_phase") == 0) {
+        ns_spectral_initialize_random_phase(data, (unsigned long long)ns_config_get_int(&cfg, "init.seed", 7),
+                                            ns_config_get_double(&cfg, "init.k0", 8.0),
+                                            ns_config_get_double(&cfg, "init.max_omega", 5.0));
+    } else {
+        ns_spectral_initialize_taylor_green(data);
+    }
+
+    NSSpectralHyperviscosityConfig hv;
+    ns_spectral_hyperviscosity_default(&hv);
+    hv.coefficient = ns_config_get_double(&cfg, "spectral.hyperviscosity.coefficient", 0.0);
+    hv.enabled = hv.coefficient > 0.0;
+    hv.order = ns_config_get_int(&cfg, "spectral.hyperviscosity.order", 8);
+    hv.cutoff_ratio = ns_config_get_double(&cfg, "spectral.hyperviscosity.cutoff_ratio", 0.65);
+    hv.sfd_strength = ns_config_get_double(&cfg, "spectral.sfd.strength", 0.0);
+    hv.sfd_enabled = hv.sfd_strength > 0.0;
+    hv.sfd_timescale = ns_config_get_double(&cfg, "spectral.sfd.timescale", 1.0);
+    ns_spectral_hyperviscosity_set(data, &hv);
+
+    NSForcingState forcing;
+    NSForcingState *fs = NULL;
+    const char *ftype = ns_config_get_string(&cfg, "forcing.type", "none");
+    if (strcmp(ftype, "none") != 0) {
+        NSForcingConfig fc;
+        ns_forcing_config_default(&fc);
+        fc.type = (strcmp(ftype, "colored") == 0) ? NS_FORCING_COLORED_NOISE : NS_FORCING_WHITE_NOISE;
+        fc.energy_target = ns_config_get_double(&cfg, "forcing.energy_target", 1.0);
+        fc.correlation_time = ns_config_get_double(&cfg, "forcing.correlation_time", 0.5);
+        fc.seed = (unsigned long)ns_config_get_int(&cfg, "forcing.seed", 0);
+        fc.kmin = ns_config_get_double(&cfg, "forcing.kmin", 0.0);
+        fc.kmax = ns_config_get_double(&cfg, "forcing.kmax", 4.0);
+        if (ns_forcing_state_init(&forcing, &fc, data->k2, data->nkx, data->nky) != 0) {
+            fprintf(stderr, "forcing band [%g, %g] contains no mode\n", fc.kmin, fc.kmax);
+            ns_spectral_free(data);
+            return 2;
+        }
+        fs = &forcing;
+    }
+
+    ns_spectral_compute_derivatives(data); /* canonical start: psi_hat defined */
+    printf("Initial conditions:\n");
+    printf("Energy: %.6e\n", ns_spectral_compute_energy(data));
+    printf("Enstrophy: %.6e\n\n", ns_spectral_compute_enstrophy(data));
+
+    ns_spectral_set_sync_policy(data, NS_SYNC_LAZY);
+    const double t0 = now_seconds();
+    int step = 0, resolution_adequate = 1;
+    while (data->t < t_final && resolution_adequate && (max_steps <= 0 || step < max_steps)) {
+        /* batches of 10 steps between console lines; single steps near t_end so the loop
+         * stops on the same step as the reference's per-step test */
+        int chunk = 10 - step % 10;
+        if (data->dt > 0.0 && (t_final - data->t) < 2.0 * chunk * data->dt) chunk = 1;
+        if (step == 0) chunk = 1;
+        if (max_steps > 0 && step + chunk > max_steps) chunk = max_steps - step;
+        if (ns_spectral_run_steps(data, chunk, fs) != 0) {
+            fprintf(stderr, "run_steps failed: %s\n", ns_spectral_last_error());
+            break;
+        }
+        step += chunk;
+        ns_spectral_analyze_convergence(data, step);
+        if (step % 100 == 0) resolution_adequate = ns_spectral_check_resolution(data);
+        if (output_interval > 0 && step % output_interval == 0) {
+            char filename[512];
+            snprintf(filename, sizeof filename, "%s_step_%04d.dat", prefix, step);
+            ns_spectral_output_solution(data, filename);
+            if (step % (5 * output_interval) == 0) ns_spectral_analyze_spectrum(data);
+        }
+        if (data->dt < MIN_DT) {
+            printf("Time step too small!\n");
+            break;
+        }
+    }
+    ns_spectral_sync_to_host(data, NS_FIELD_OMEGA_HAT);
+    const double wall = now_seconds() - t0;
+
+    printf("\n=== SIMULATION COMPLETED ===\n");
+    printf("Total steps: %d\n", step);
+    printf("Final time: %.6f\n", data->t);
+    printf("Final energy: %.6e\n", ns_spectral_compute_energy(data));
+    printf("Final enstrophy: %.6e\n", ns_spectral_compute_enstrophy(data));
+    printf("Wall time: %.2f seconds\n", wall);
+    printf("Steps/second: %.1f\n", step / (wall > 0 ? wall : 1e-9));
+    printf("Grid-point-steps/second: %.3e\n\n", (double)nx * ny * step / (wall > 0 ? wall : 1e-9));
+
+    if (output_interval > 0) {
+        char filename[512];
+        snprintf(filename, sizeof filename, "%s_final.dat", prefix);
+        ns_spectral_output_solution(data, filename);
+    }
+    ns_spectral_analyze_spectrum(data);
+
+    printf("\nSpectral Accuracy:\n");
+    if (ns_spectral_check_resolution(data)) {
+        printf("✓ Resolution adequate\n");
+        printf("✓ High-order accuracy maintained\n");
+    } else {
+        printf("⚠ Consider increasing resolution\n");
+    }
+
+    if (fs) ns_forcing_state_free(fs);
+    ns_spectral_free(data);
+    ns_config_free(&cfg);
+    return 0;
+}

@@ -1,0 +1,811 @@
+/*
+ * spectral_api.c -- the spectral solver's C entry points (include/ns_spectral_solver.h)
+ * implemented over the kernel C-ABI (include/nsb.h). Host C, no numerics of its own
+ * beyond setup tables and driver diagnostics: every transform, operator, reduction and
+ * RK stage runs in the sm_100a kernels. No CPU fallback.
+ *
+ * Each function cites the reference function it replaces
+ * (/root/reference/src/spectral/...). See the header for the EAGER / LAZY coherence
+ * policy.
+ */
+#include "ns_spectral_solver.h"
+#include "nsb.h"
+
+#include <stdarg.h>
+
+typedef struct {
+    nsb_ctx *ctx;
+    int device;
+    NSSyncPolicy policy;
+    /* forcing fast path: ascending active-index list of the last NSForcingState seen */
+    const NSForcingState *forcing_owner;
+    int *forcing_idx;
+    int forcing_n, ib, jb;
+    double _Complex *forcing_box;
+} Backend;
+
+static _Thread_local char g_error[512] = "";
+
+static void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+
+const char *ns_spectral_last_error(void) { return g_error; }
+
+static Backend *backend_of(const NSSpectralData *d) { return d ? (Backend *)d->backend : NULL; }
+
+/* loud failure: the reference's entry points return void, so an unusable device cannot
+ * be reported through them -- and must never degrade into a silent CPU path. */
+static void die(const char *where, const char *why) {
+    fprintf(stderr, "ns_spectral (B200 backend): %s: %s\n", where, why);
+    abort();
+}
+
+static nsb_ctx *ctx_of(NSSpectralData *d, const char *where) {
+    Backend *b = backend_of(d);
+    if (!d || !b) die(where, "NULL solver data");
+    if (!b->ctx) die(where, "no device context: call ns_spectral_initialize_fft_plans() on a machine with a "
+                            "CUDA device first (there is no CPU fallback)");
+    return b->ctx;
+}
+
+#define NSB_OK(call, where)                               \
+    do {                                                  \
+        if ((call) != 0) die(where, nsb_last_error());    \
+    } while (0)
+
+static size_t n_phys(const NSSpectralData *d) { return (size_t)d->nx * (size_t)d->ny; }
+static size_t n_spec(const NSSpectralData *d) { return (size_t)d->nkx * (size_t)d->nky; }
+static int lazy(const NSSpectralData *d) { return backend_of(d)->policy == NS_SYNC_LAZY; }
+
+/* ------------------------------------------------------------------ memory */
+
+/* calloc: large arrays come from fresh zero pages and cost nothing until touched
+ * (the struct carries 138 bytes per grid point, 37 GB at 16384^2) */
+static void *zalloc64(size_t bytes) { return calloc(bytes ? bytes : 16, 1); }
+
+/* spectral_memory.c:6-68. All arrays zero-filled (the reference leaves them
+ * uninitialised). */
+NSSpectralData *ns_spectral_allocate(int nx, int ny, double Lx, double Ly, double Re) {
+    if (nx <= 0 || ny <= 0) return NULL;
+    NSSpectralData *d = (NSSpectralData *)calloc(1, sizeof *d);
+    if (!d) return NULL;
+    d->nx = nx; d->ny = ny; d->nkx = nx / 2 + 1; d->nky = ny;
+    d->Lx = Lx; d->Ly = Ly; d->Re = Re;
+    d->dt = 0.01; d->t = 0.0; d->cfl_factor = 0.3;
+    const size_t n = n_phys(d), m = n_spec(d);
+    double **re[] = {&d->u, &d->v, &d->p, &d->omega, &d->psi};
+    fftw_complex **cx[] = {&d->u_hat, &d->v_hat, &d->omega_hat, &d->psi_hat, &d->nonlinear_hat, &d->rk1_hat,
+                           &d->rk2_hat, &d->rk3_hat, &d->rk4_hat, &d->omega_tmp_hat, &d->sfd_hat};
+    int ok = 1;
+    for (size_t k = 0; k < sizeof re / sizeof re[0]; ++k) ok &= ((*re[k] = (double *)zalloc64(n * sizeof(double))) != NULL);
+    for (size_t k = 0; k < sizeof cx / sizeof cx[0]; ++k) ok &= ((*cx[k] = (fftw_complex *)zalloc64(m * sizeof(fftw_complex))) != NULL);
+    d->x = (double *)calloc((size_t)nx, sizeof(double));
+    d->y = (double *)calloc((size_t)ny, sizeof(double));
+    d->kx = (double *)calloc((size_t)d->nkx, sizeof(double));
+    d->ky = (double *)calloc((size_t)d->nky, sizeof(double));
+    d->k2 = (double *)calloc(m, sizeof(double));
+    d->dealias_mask = (int *)calloc(m, sizeof(int));
+    d->hyperviscosity_weights = (double *)calloc(m, sizeof(double));
+    Backend *b = (Backend *)calloc(1, sizeof *b);
+    d->backend = b;
+    if (!ok || !d->x || !d->y || !d->kx || !d->ky || !d->k2 || !d->dealias_mask || !d->hyperviscosity_weights || !b) {
+        ns_spectral_free(d);
+        return NULL;
+    }
+    const char *env = getenv("NS_SPECTRAL_DEVICE");
+    b->device = env ? atoi(env) : 0;
+    b->policy = NS_SYNC_EAGER;
+    ns_spectral_hyperviscosity_default(&d->hyperviscosity);
+    return d;
+}
+
+/* spectral_memory.c:71-104 (no global fftw_cleanup: instances are independent here) */
+void ns_spectral_free(NSSpectralData *d) {
+    if (!d) return;
+    Backend *b = backend_of(d);
+    if (b) {
+        if (b->ctx) nsb_ctx_destroy(b->ctx);
+        free(b->forcing_idx);
+        free(b->forcing_box);
+        free(b);
+    }
+    free(d->u); free(d->v); free(d->p); free(d->omega); free(d->psi);
+    free(d->u_hat); free(d->v_hat); free(d->omega_hat); free(d->psi_hat); free(d->nonlinear_hat);
+    free(d->rk1_hat); free(d->rk2_hat); free(d->rk3_hat); free(d->rk4_hat); free(d->omega_tmp_hat);
+    free(d->sfd_hat);
+    free(d->x); free(d->y); free(d->kx); free(d->ky); free(d->k2);
+    free(d->dealias_mask); free(d->hyperviscosity_weights);
+    free(d);
+}
+
+/* ---------------------------------------------------------- initialisation */
+
+/* spectral_initialization.c:10-54 (host tables; the kernels rebuild kx, ky, k2 and the
+ * mask from indices with the same formulas) */
+void ns_spectral_initialize_grids(NSSpectralData *d) {
+    if (!d) return;
+    const int nx = d->nx, ny = d->ny, nkx = d->nkx, nky = d->nky;
+    for (int i = 0; i < nx; ++i) d->x[i] = i * d->Lx / nx;
+    for (int j = 0; j < ny; ++j) d->y[j] = j * d->Ly / ny;
+    for (int i = 0; i < nkx; ++i) d->kx[i] = 2.0 * M_PI * i / d->Lx;
+    for (int j = 0; j < nky; ++j)
+        d->ky[j] = (j <= ny / 2) ? 2.0 * M_PI * j / d->Ly : 2.0 * M_PI * (j - ny) / d->Ly;
+    const int xcut = (2 * nkx) / 3, ycut = (2 * ny) / 6;
+    for (int j = 0; j < nky; ++j) {
+        const int band = (j <= ny / 2) ? j : j - ny;
+        for (int i = 0; i < nkx; ++i) {
+            const size_t idx = (size_t)j * nkx + i;
+            d->k2[idx] = d->kx[i] * d->kx[i] + d->ky[j] * d->ky[j];
+            d->dealias_mask[idx] = (i <= xcut) && (abs(band) <= ycut);
+        }
+    }
+    ns_spectral_hyperviscosity_update_weights(d);
+}
+
+static void push_hyperviscosity(NSSpectralData *d) {
+    Backend *b = backend_of(d);
+    if (!b || !b->ctx) return;
+    const NSSpectralHyperviscosityConfig *h = &d->hyperviscosity;
+    nsb_hyperviscosity p;
+    p.enabled = (h->enabled && h->coefficient > 0.0);
+    p.coefficient = h->coefficient;
+    p.order = h->order > 0 ? h->order : 1;
+    p.cutoff_wavenumber = h->cutoff_wavenumber;
+    p.inv_bandwidth = h->inv_bandwidth;
+    p.sfd_enabled = (h->sfd_enabled && h->sfd_strength > 0.0);
+    p.sfd_strength = h->sfd_strength;
+    p.sfd_timescale = h->sfd_timescale;
+    NSB_OK(nsb_set_hyperviscosity(b->ctx, &p), "hyperviscosity");
+}
+
+/* spectral_initialization.c:57-69: "plan creation" = device context creation */
+void ns_spectral_initialize_fft_plans(NSSpectralData *d) {
+    Backend *b = backend_of(d);
+    if (!d || !b) return;
+    if (b->ctx) return;
+    nsb_params p;
+    memset(&p, 0, sizeof p);
+    p.nx = d->nx; p.ny = d->ny; p.Lx = d->Lx; p.Ly = d->Ly; p.Re = d->Re;
+    p.cfl_factor = d->cfl_factor;
+    p.device = b->device;
+    if (nsb_ctx_create(&p, &b->ctx) != 0) {
+        set_error("%s", nsb_last_error());
+        fprintf(stderr, "ns_spectral (B200 backend): cannot create device context: %s\n", nsb_last_error());
+        b->ctx = NULL;
+        d->forward_plan = d->backward_plan = NULL;
+        return;
+    }
+    d->forward_plan = d->backward_plan = (fftw_plan)b->ctx;
+    push_hyperviscosity(d);
+}
+
+static void upload(NSSpectralData *d, int field, const void *host, const char *where) {
+    NSB_OK(nsb_upload(ctx_of(d, where), field, host), where);
+}
+static void download(NSSpectralData *d, int field, void *host, const char *where) {
+    NSB_OK(nsb_download(ctx_of(d, where), field, host), where);
+}
+
+/* device: psi_hat,u_hat,v_hat,u,v,omega from omega_hat; host arrays refreshed */
+static void refresh_derived_to_host(NSSpectralData *d, const char *where) {
+    nsb_ctx *c = ctx_of(d, where);
+    NSB_OK(nsb_compute_derivatives(c), where);
+    download(d, NSB_PSI_HAT, d->psi_hat, where);
+    download(d, NSB_U_HAT, d->u_hat, where);
+    download(d, NSB_V_HAT, d->v_hat, where);
+    download(d, NSB_U, d->u, where);
+    download(d, NSB_V, d->v, where);
+    download(d, NSB_OMEGA, d->omega, where);
+}
+
+/* spectral_initialization.c:72-95 (the inconsistent omega of G8 is kept: parity) */
+void ns_spectral_initialize_taylor_green(NSSpectralData *d) {
+    static const char *W = "ns_spectral_initialize_taylor_green";
+    nsb_ctx *c = ctx_of(d, W);
+    const int nx = d->nx, ny = d->ny;
+    const double Lx = d->Lx, Ly = d->Ly;
+    for (int j = 0; j < ny; ++j) {
+        for (int i = 0; i < nx; ++i) {
+            const size_t idx = (size_t)j * nx + i;
+            const double x = d->x[i], y = d->y[j];
+            d->u[idx] = sin(2 * M_PI * x / Lx) * cos(2 * M_PI * y / Ly);
+            d->v[idx] = -cos(2 * M_PI * x / Lx) * sin(2 * M_PI * y / Ly);
+            d->omega[idx] = 2.0 * (2 * M_PI / Lx) * cos(2 * M_PI * x / Lx) * cos(2 * M_PI * y / Ly);
+            d->p[idx] = 0.0;
+        }
+    }
+    upload(d, NSB_OMEGA, d->omega, W);
+    upload(d, NSB_U, d->u, W);
+    upload(d, NSB_V, d->v, W);
+    NSB_OK(nsb_physical_to_spectral(c, NSB_OMEGA, NSB_OMEGA_HAT), W);
+    NSB_OK(nsb_physical_to_spectral(c, NSB_U, NSB_U_HAT), W);
+    NSB_OK(nsb_physical_to_spectral(c, NSB_V, NSB_V_HAT), W);
+    download(d, NSB_OMEGA_HAT, d->omega_hat, W);
+    download(d, NSB_U_HAT, d->u_hat, W);
+    download(d, NSB_V_HAT, d->v_hat, W);
+}
+
+static unsigned long long sm64(unsigned long long *st) {
+    unsigned long long z = (*st += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+/* SURVEY 8d (build-defined; the reference has no turbulence initial condition) */
+int ns_spectral_initialize_random_phase(NSSpectralData *d, unsigned long long seed, double k0, double max_omega) {
+    static const char *W = "ns_spectral_initialize_random_phase";
+    nsb_ctx *c = ctx_of(d, W);
+    const int nkx = d->nkx, nky = d->nky, ny = d->ny;
+    unsigned long long st = seed;
+    for (int j = 0; j < nky; ++j) {
+        const int band = (j <= ny / 2) ? j : j - ny;
+        for (int i = 0; i < nkx; ++i) {
+            const double un = (double)(sm64(&st) >> 11) * (1.0 / 9007199254740992.0);
+            const double theta = 2.0 * M_PI * un;
+            const double kk = sqrt((double)i * i + (double)band * band);
+            const double a = kk * kk * exp(-(kk / k0) * (kk / k0));
+            d->omega_hat[(size_t)j * nkx + i] = a * cos(theta) + I * (a * sin(theta));
+        }
+    }
+    d->omega_hat[0] = 0.0;
+    upload(d, NSB_OMEGA_HAT, d->omega_hat, W);
+    const int src = NSB_OMEGA_HAT, dst = NSB_OMEGA;
+    NSB_OK(nsb_spectral_to_physical(c, 1, &src, &dst), W);
+    download(d, NSB_OMEGA, d->omega, W);
+    double peak = 0.0;
+    const size_t n = n_phys(d);
+    for (size_t k = 0; k < n; ++k) peak = fmax(peak, fabs(d->omega[k]));
+    const double scale = (peak > 0.0) ? max_omega / peak : 0.0;
+    for (size_t k = 0; k < n; ++k) d->omega[k] *= scale;
+    upload(d, NSB_OMEGA, d->omega, W);
+    NSB_OK(nsb_physical_to_spectral(c, NSB_OMEGA, NSB_OMEGA_HAT), W);
+    download(d, NSB_OMEGA_HAT, d->omega_hat, W);
+    refresh_derived_to_host(d, W);
+    return 0;
+}
+
+/* -------------------------------------------------------------- transforms */
+
+/* spectral_transforms.c:9-22 */
+void ns_spectral_physical_to_spectral(NSSpectralData *d, double *field, fftw_complex *field_hat) {
+    static const char *W = "ns_spectral_physical_to_spectral";
+    nsb_ctx *c = ctx_of(d, W);
+    if (!field || !field_hat) return;
+    upload(d, NSB_SCRATCH_PHYS, field, W);
+    const int dst = (field_hat == d->omega_hat) ? NSB_OMEGA_HAT : NSB_SCRATCH_HAT;
+    NSB_OK(nsb_physical_to_spectral(c, NSB_SCRATCH_PHYS, dst), W);
+    download(d, dst, field_hat, W);
+}
+
+/* spectral_transforms.c:25-32 (the caller's field_hat is left untouched; the
+ * reference's use of nonlinear_hat as scratch is not reproduced) */
+void ns_spectral_spectral_to_physical(NSSpectralData *d, fftw_complex *field_hat, double *field) {
+    static const char *W = "ns_spectral_spectral_to_physical";
+    nsb_ctx *c = ctx_of(d, W);
+    if (!field_hat || !field) return;
+    upload(d, NSB_SCRATCH_HAT, field_hat, W);
+    const int src = NSB_SCRATCH_HAT, dst = NSB_SCRATCH_PHYS;
+    NSB_OK(nsb_spectral_to_physical(c, 1, &src, &dst), W);
+    download(d, NSB_SCRATCH_PHYS, field, W);
+}
+
+/* spectral_transforms.c:35-43 */
+void ns_spectral_apply_dealiasing(NSSpectralData *d, fftw_complex *field_hat) {
+    static const char *W = "ns_spectral_apply_dealiasing";
+    nsb_ctx *c = ctx_of(d, W);
+    if (!field_hat) return;
+    if (lazy(d) && field_hat == d->omega_hat) {
+        NSB_OK(nsb_apply_dealiasing(c, NSB_OMEGA_HAT), W);
+        return;
+    }
+    upload(d, NSB_SCRATCH_HAT, field_hat, W);
+    NSB_OK(nsb_apply_dealiasing(c, NSB_SCRATCH_HAT), W);
+    download(d, NSB_SCRATCH_HAT, field_hat, W);
+}
+
+/* -------------------------------------------------------------------- core */
+
+/* spectral_core.c:8-34 */
+void ns_spectral_compute_velocity_from_vorticity(NSSpectralData *d) {
+    static const char *W = "ns_spectral_compute_velocity_from_vorticity";
+    nsb_ctx *c = ctx_of(d, W);
+    if (!lazy(d)) upload(d, NSB_OMEGA_HAT, d->omega_hat, W);
+    NSB_OK(nsb_velocity_from_vorticity(c), W);
+    if (!lazy(d)) {
+        download(d, NSB_PSI_HAT, d->psi_hat, W);
+        download(d, NSB_U_HAT, d->u_hat, W);
+        download(d, NSB_V_HAT, d->v_hat, W);
+    }
+}
+
+/* spectral_core.c:37-43 */
+void ns_spectral_compute_derivatives(NSSpectralData *d) {
+    static const char *W = "ns_spectral_compute_derivatives";
+    nsb_ctx *c = ctx_of(d, W);
+    if (lazy(d)) {
+        NSB_OK(nsb_compute_derivatives(c), W);
+        return;
+    }
+    upload(d, NSB_OMEGA_HAT, d->omega_hat, W);
+    refresh_derived_to_host(d, W);
+}
+
+/* spectral_core.c:46-112: nonlinear_hat from the STORED psi_hat and omega_hat */
+void ns_spectral_compute_nonlinear_terms(NSSpectralData *d) {
+    static const char *W = "ns_spectral_compute_nonlinear_terms";
+    nsb_ctx *c = ctx_of(d, W);
+    if (!lazy(d)) {
+        upload(d, NSB_PSI_HAT, d->psi_hat, W);
+        upload(d, NSB_OMEGA_HAT, d->omega_hat, W);
+    }
+    NSB_OK(nsb_nonlinear_terms(c), W);
+    if (!lazy(d)) download(d, NSB_NONLINEAR_HAT, d->nonlinear_hat, W);
+}
+
+/* --------------------------------------------------------- time integration */
+
+/* spectral_time_integration.c:9-31 */
+double ns_spectral_compute_cfl_timestep(NSSpectralData *d) {
+    static const char *W = "ns_spectral_compute_cfl_timestep";
+    nsb_ctx *c = ctx_of(d, W);
+    double dt = 0.0;
+    if (lazy(d)) {
+        NSB_OK(nsb_cfl_timestep(c, &dt), W);
+    } else {
+        upload(d, NSB_U, d->u, W);
+        upload(d, NSB_V, d->v, W);
+        NSB_OK(nsb_cfl_timestep_uv(c, &dt), W);
+    }
+    return dt;
+}
+
+static int push_sfd_if_needed(NSSpectralData *d, const char *where) {
+    const NSSpectralHyperviscosityConfig *h = &d->hyperviscosity;
+    if (h->sfd_enabled && h->sfd_strength > 0.0) {
+        upload(d, NSB_SFD_HAT, d->sfd_hat, where);
+        return 1;
+    }
+    return 0;
+}
+
+/* dense forcing array -> bounding box of its non-zero entries -> device */
+static void push_dense_forcing(NSSpectralData *d, const fftw_complex *f, const char *where) {
+    nsb_ctx *c = ctx_of(d, where);
+    if (!f) {
+        NSB_OK(nsb_set_forcing(c, 0, 0, NULL), where);
+        return;
+    }
+    int ib = 0, jb = 0;
+    for (int j = 0; j < d->nky; ++j) {
+        const int band = (j <= d->ny / 2) ? j : j - d->ny;
+        for (int i = 0; i < d->nkx; ++i) {
+            const fftw_complex v = f[(size_t)j * d->nkx + i];
+            if (creal(v) != 0.0 || cimag(v) != 0.0) {
+                if (i > ib) ib = i;
+                if (abs(band) > jb) jb = abs(band);
+            }
+        }
+    }
+    if (jb >= d->ny / 2) jb = d->ny / 2 - 1;
+    const size_t cells = (size_t)(2 * jb + 1) * (size_t)(ib + 1);
+    double _Complex *box = (double _Complex *)calloc(cells, sizeof *box);
+    if (!box) die(where, "out of memory");
+    for (int band = -jb; band <= jb; ++band) {
+        const int j = (band >= 0) ? band : band + d->ny;
+        for (int i = 0; i <= ib; ++i) box[(size_t)(band + jb) * (ib + 1) + i] = f[(size_t)j * d->nkx + i];
+    }
+    NSB_OK(nsb_set_forcing(c, ib, jb, (const double *)box), where);
+    free(box);
+}
+
+/* spectral_time_integration.c:34-106 (+ f_hat) */
+int ns_spectral_advance_rk4_forced(NSSpectralData *d, const fftw_complex *forcing) {
+    static const char *W = "ns_spectral_advance_rk4";
+    nsb_ctx *c = ctx_of(d, W);
+    if (!(d->dt > 0.0)) {
+        set_error("advance_rk4: data->dt must be positive (got %g)", d->dt);
+        return -1;
+    }
+    int sfd = 0;
+    if (!lazy(d)) {
+        upload(d, NSB_OMEGA_HAT, d->omega_hat, W);
+        sfd = push_sfd_if_needed(d, W);
+    }
+    push_dense_forcing(d, forcing, W);
+    NSB_OK(nsb_rk4_step(c, d->dt), W);
+    d->t += d->dt;
+    if (!lazy(d)) {
+        download(d, NSB_OMEGA_HAT, d->omega_hat, W);
+        if (sfd) download(d, NSB_SFD_HAT, d->sfd_hat, W);
+        refresh_derived_to_host(d, W);
+    }
+    NSB_OK(nsb_set_time(c, d->t), W);
+    return 0;
+}
+
+void ns_spectral_advance_rk4(NSSpectralData *d) {
+    if (ns_spectral_advance_rk4_forced(d, NULL) != 0) die("ns_spectral_advance_rk4", g_error);
+}
+
+static int bind_forcing(NSSpectralData *d, NSForcingState *fs) {
+    Backend *b = backend_of(d);
+    if (b->forcing_owner == fs && b->forcing_idx) return 0;
+    free(b->forcing_idx);
+    free(b->forcing_box);
+    b->forcing_idx = NULL;
+    b->forcing_box = NULL;
+    b->forcing_owner = NULL;
+    if (fs->nkx != d->nkx || fs->nky != d->nky || fs->active_modes <= 0) {
+        set_error("forcing state does not match the solver grid");
+        return -1;
+    }
+    b->forcing_idx = (int *)malloc((size_t)fs->active_modes * sizeof(int));
+    if (!b->forcing_idx || ns_forcing_active_indices(fs, b->forcing_idx) != 0 ||
+        ns_forcing_box_extent(fs, &b->ib, &b->jb) != 0) {
+        set_error("cannot index the forcing band");
+        return -1;
+    }
+    if (b->jb >= d->ny / 2) b->jb = d->ny / 2 - 1;
+    b->forcing_box = (double _Complex *)malloc((size_t)(2 * b->jb + 1) * (size_t)(b->ib + 1) * sizeof(double _Complex));
+    if (!b->forcing_box) return -1;
+    b->forcing_n = fs->active_modes;
+    b->forcing_owner = fs;
+    return 0;
+}
+
+/* main_spectral.c:46-48 n times, device resident */
+int ns_spectral_run_steps(NSSpectralData *d, int n, NSForcingState *fs) {
+    static const char *W = "ns_spectral_run_steps";
+    nsb_ctx *c = ctx_of(d, W);
+    Backend *b = backend_of(d);
+    if (n < 0) return -1;
+    int sfd = 0;
+    if (!lazy(d)) {
+        upload(d, NSB_OMEGA_HAT, d->omega_hat, W);
+        sfd = push_sfd_if_needed(d, W);
+    }
+    NSB_OK(nsb_set_time(c, d->t), W);
+    if (fs && bind_forcing(d, fs) != 0) return -1;
+    if (!fs) NSB_OK(nsb_set_forcing(c, 0, 0, NULL), W);
+    for (int s = 0; s < n; ++s) {
+        double dt = 0.0; /* 0 = CFL step computed on the device inside the step */
+        if (fs) {
+            /* coloured noise needs dt before the stream is consumed (forcing.c:138-147) */
+            if (fs->config.type == NS_FORCING_COLORED_NOISE) NSB_OK(nsb_cfl_timestep(c, &dt), W);
+            ns_forcing_generate_box(fs, dt, b->forcing_idx, b->ib, b->jb, b->forcing_box);
+            NSB_OK(nsb_set_forcing(c, b->ib, b->jb, (const double *)b->forcing_box), W);
+        }
+        NSB_OK(nsb_rk4_step(c, dt), W);
+    }
+    int steps = 0;
+    NSB_OK(nsb_get_state(c, &d->dt, &d->t, &steps), W);
+    if (!lazy(d)) {
+        download(d, NSB_OMEGA_HAT, d->omega_hat, W);
+        if (sfd) download(d, NSB_SFD_HAT, d->sfd_hat, W);
+        refresh_derived_to_host(d, W);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------- diagnostics */
+
+static void sums(NSSpectralData *d, double out[4], const char *where) {
+    nsb_ctx *c = ctx_of(d, where);
+    if (lazy(d)) {
+        NSB_OK(nsb_diagnostics(c, out), where);
+    } else {
+        upload(d, NSB_U, d->u, where);
+        upload(d, NSB_V, d->v, where);
+        upload(d, NSB_OMEGA, d->omega, where);
+        NSB_OK(nsb_diagnostics_phys(c, out), where);
+    }
+}
+
+/* spectral_analysis.c:8-19 */
+double ns_spectral_compute_energy(NSSpectralData *d) {
+    double s[4];
+    sums(d, s, "ns_spectral_compute_energy");
+    return 0.5 * (s[0] + s[1]) / (d->nx * d->ny);
+}
+
+/* spectral_analysis.c:22-33 */
+double ns_spectral_compute_enstrophy(NSSpectralData *d) {
+    double s[4];
+    sums(d, s, "ns_spectral_compute_enstrophy");
+    return 0.5 * s[2] / (d->nx * d->ny);
+}
+
+static void lazy_fetch_spectra(NSSpectralData *d, int with_velocity, const char *where) {
+    if (!lazy(d)) return;
+    download(d, NSB_OMEGA_HAT, d->omega_hat, where);
+    if (with_velocity) {
+        NSB_OK(nsb_velocity_from_vorticity(ctx_of(d, where)), where);
+        download(d, NSB_U_HAT, d->u_hat, where);
+        download(d, NSB_V_HAT, d->v_hat, where);
+    }
+}
+
+/* spectral_analysis.c:36-66 */
+int ns_spectral_check_resolution(NSSpectralData *d) {
+    static const char *W = "ns_spectral_check_resolution";
+    ctx_of(d, W);
+    lazy_fetch_spectra(d, 0, W);
+    const size_t m = n_spec(d);
+    const double max_k = sqrt(d->k2[m - 1]);
+    double high = 0.0, total = 0.0;
+    for (size_t k = 0; k < m; ++k) {
+        const double a = cabs(d->omega_hat[k]);
+        const double mag2 = a * a;
+        total += mag2;
+        const double kn = (max_k > 0.0) ? sqrt(d->k2[k]) / max_k : 0.0;
+        if (kn > 0.8) high += mag2;
+    }
+    const double frac = (total > 1e-16) ? high / total : 0.0;
+    if (frac > 1e-6) {
+        printf("Warning: %.2e%% of energy in high wavenumbers\n", frac * 100);
+        return 0;
+    }
+    return 1;
+}
+
+/* spectral_analysis.c:69-100 */
+void ns_spectral_analyze_convergence(NSSpectralData *d, int step) {
+    static const char *W = "ns_spectral_analyze_convergence";
+    if (step % 10 != 0) return;
+    ctx_of(d, W);
+    double s[4];
+    sums(d, s, W);
+    const double energy = 0.5 * (s[0] + s[1]) / (d->nx * d->ny);
+    const double enstrophy = 0.5 * s[2] / (d->nx * d->ny);
+    lazy_fetch_spectra(d, 0, W);
+    const size_t m = n_spec(d);
+    const double cut = 0.25 * d->k2[m - 1];
+    double peak = 0.0, tail = 0.0;
+    long high = 0;
+    for (size_t k = 0; k < m; ++k) {
+        const double a = cabs(d->omega_hat[k]);
+        if (a > peak) peak = a;
+        if (d->k2[k] > cut) {
+            tail += a * a;
+            ++high;
+        }
+    }
+    const double err = high > 0 ? sqrt(tail / (double)high) : 0.0;
+    printf("Step %d: t=%.4f, E=%.6e, Ω=%.6e, max|ω̂|=%.2e, err=%.2e, dt=%.2e\n", step, d->t, energy, enstrophy,
+           peak, err, d->dt);
+}
+
+/* spectral_analysis.c:103-142 */
+void ns_spectral_analyze_spectrum(NSSpectralData *d) {
+    static const char *W = "ns_spectral_analyze_spectrum";
+    ctx_of(d, W);
+    lazy_fetch_spectra(d, 1, W);
+    const int nkx = d->nkx, nky = d->nky;
+    const int max_k = (int)fmin(nkx, nky / 2);
+    double *ek = (double *)calloc((size_t)max_k, sizeof(double));
+    int *cnt = (int *)calloc((size_t)max_k, sizeof(int));
+    if (!ek || !cnt) {
+        free(ek);
+        free(cnt);
+        return;
+    }
+    for (size_t k = 0; k < n_spec(d); ++k) {
+        const int bin = (int)(sqrt(d->k2[k]) + 0.5);
+        if (bin < max_k) {
+            const double a = cabs(d->u_hat[k]), b = cabs(d->v_hat[k]);
+            ek[bin] += 0.5 * (a * a + b * b);
+            cnt[bin]++;
+        }
+    }
+    printf("\nEnergy Spectrum (t=%.4f):\n", d->t);
+    printf("k\tE(k)\t\tSlope\n");
+    for (int k = 1; k < max_k && cnt[k] > 0; ++k) {
+        ek[k] /= cnt[k];
+        double slope = 0.0;
+        if (k > 1 && ek[k - 1] > 1e-16 && ek[k] > 1e-16) slope = log(ek[k] / ek[k - 1]) / log((double)k / (k - 1));
+        if (k <= 10 || k % 5 == 0) printf("%d\t%.2e\t%.2f\n", k, ek[k], slope);
+    }
+    free(ek);
+    free(cnt);
+}
+
+/* ---------------------------------------------------------- hyperviscosity */
+
+static double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* hyperviscosity.c:15-30 */
+void ns_spectral_hyperviscosity_default(NSSpectralHyperviscosityConfig *c) {
+    if (!c) return;
+    memset(c, 0, sizeof *c);
+    c->order = 8;
+    c->cutoff_ratio = 0.65;
+    c->sfd_timescale = 1.0;
+}
+
+/* hyperviscosity.c:60-102 (host table kept for callers that read it; the kernels
+ * evaluate the same formula per mode) */
+void ns_spectral_hyperviscosity_update_weights(NSSpectralData *d) {
+    if (!d || !d->hyperviscosity_weights || !d->k2) return;
+    const size_t m = n_spec(d);
+    NSSpectralHyperviscosityConfig *h = &d->hyperviscosity;
+    double kmax = 0.0;
+    for (size_t k = 0; k < m; ++k) kmax = fmax(kmax, sqrt(d->k2[k]));
+    h->kmax = kmax;
+    h->cutoff_wavenumber = clampd(h->cutoff_ratio, 0.0, 1.0) * kmax;
+    const double bw = fmax(kmax - h->cutoff_wavenumber, 1e-12);
+    h->inv_bandwidth = (bw > 0.0) ? 1.0 / bw : 0.0;
+    if (!h->enabled || h->coefficient <= 0.0 || kmax <= 0.0) {
+        memset(d->hyperviscosity_weights, 0, m * sizeof(double));
+    } else {
+        const int order = h->order > 0 ? h->order : 1;
+        for (size_t k = 0; k < m; ++k) {
+            const double kmag = sqrt(d->k2[k]);
+            d->hyperviscosity_weights[k] =
+                (kmag > h->cutoff_wavenumber) ? h->coefficient * pow((kmag - h->cutoff_wavenumber) * h->inv_bandwidth, order) : 0.0;
+        }
+    }
+    push_hyperviscosity(d);
+}
+
+/* hyperviscosity.c:32-58 */
+void ns_spectral_hyperviscosity_set(NSSpectralData *d, const NSSpectralHyperviscosityConfig *cfg) {
+    if (!d || !cfg) return;
+    const size_t m = n_spec(d);
+    d->hyperviscosity = *cfg;
+    NSSpectralHyperviscosityConfig *h = &d->hyperviscosity;
+    if (!h->enabled) memset(d->hyperviscosity_weights, 0, m * sizeof(double));
+    if (!h->sfd_enabled || h->sfd_strength <= 0.0) {
+        h->sfd_enabled = 0;
+        h->sfd_strength = 0.0;
+        memset(d->sfd_hat, 0, m * sizeof(fftw_complex));
+    }
+    ns_spectral_hyperviscosity_update_weights(d);
+    if (h->sfd_enabled) {
+        Backend *b = backend_of(d);
+        if (b && b->ctx && lazy(d)) {
+            NSB_OK(nsb_copy(b->ctx, NSB_SFD_HAT, NSB_OMEGA_HAT), "ns_spectral_hyperviscosity_set");
+        } else {
+            memcpy(d->sfd_hat, d->omega_hat, m * sizeof(fftw_complex));
+            if (b && b->ctx) upload(d, NSB_SFD_HAT, d->sfd_hat, "ns_spectral_hyperviscosity_set");
+        }
+    }
+}
+
+/* hyperviscosity.c:104-150 */
+void ns_spectral_hyperviscosity_apply(NSSpectralData *d, fftw_complex *rhs_hat, const fftw_complex *state_hat) {
+    static const char *W = "ns_spectral_hyperviscosity_apply";
+    if (!d || !rhs_hat || !state_hat) return;
+    const NSSpectralHyperviscosityConfig *h = &d->hyperviscosity;
+    const int visc = (h->enabled && h->coefficient > 0.0), sfd = (h->sfd_enabled && h->sfd_strength > 0.0);
+    if (!visc && !sfd) return;
+    nsb_ctx *c = ctx_of(d, W);
+    push_hyperviscosity(d);
+    upload(d, NSB_SCRATCH_HAT, rhs_hat, W);
+    upload(d, NSB_SCRATCH2_HAT, state_hat, W);
+    if (sfd) upload(d, NSB_SFD_HAT, d->sfd_hat, W);
+    NSB_OK(nsb_hyperviscosity_apply(c, NSB_SCRATCH_HAT, NSB_SCRATCH2_HAT), W);
+    download(d, NSB_SCRATCH_HAT, rhs_hat, W);
+}
+
+/* hyperviscosity.c:152-178 */
+void ns_spectral_hyperviscosity_post_step(NSSpectralData *d, const fftw_complex *state_hat, double dt) {
+    static const char *W = "ns_spectral_hyperviscosity_post_step";
+    if (!d || !state_hat || dt <= 0.0) return;
+    const NSSpectralHyperviscosityConfig *h = &d->hyperviscosity;
+    if (!h->sfd_enabled || h->sfd_strength <= 0.0 || h->sfd_timescale <= 0.0) return;
+    nsb_ctx *c = ctx_of(d, W);
+    push_hyperviscosity(d);
+    upload(d, NSB_SCRATCH2_HAT, state_hat, W);
+    upload(d, NSB_SFD_HAT, d->sfd_hat, W);
+    NSB_OK(nsb_hyperviscosity_post_step(c, NSB_SCRATCH2_HAT, dt), W);
+    download(d, NSB_SFD_HAT, d->sfd_hat, W);
+}
+
+/* ------------------------------------------------------------------ output */
+
+/* spectral_output.c:4-27 */
+void ns_spectral_output_solution(NSSpectralData *d, const char *filename) {
+    static const char *W = "ns_spectral_output_solution";
+    nsb_ctx *c = ctx_of(d, W);
+    FILE *fp = fopen(filename, "w");
+    if (!fp) return;
+    if (lazy(d)) {
+        NSB_OK(nsb_compute_derivatives(c), W);
+        download(d, NSB_U, d->u, W);
+        download(d, NSB_V, d->v, W);
+        download(d, NSB_OMEGA, d->omega, W);
+    } else {
+        upload(d, NSB_PSI_HAT, d->psi_hat, W);
+    }
+    const int src = NSB_PSI_HAT, dst = NSB_PSI;
+    NSB_OK(nsb_spectral_to_physical(c, 1, &src, &dst), W);
+    download(d, NSB_PSI, d->psi, W);
+    fprintf(fp, "# Spectral Navier-Stokes Solution\n");
+    fprintf(fp, "# x y u v omega psi\n");
+    for (int j = 0; j < d->ny; ++j) {
+        for (int i = 0; i < d->nx; ++i) {
+            const size_t idx = (size_t)j * d->nx + i;
+            fprintf(fp, "%.8f %.8f %.8e %.8e %.8e %.8e\n", d->x[i], d->y[j], d->u[idx], d->v[idx], d->omega[idx],
+                    d->psi[idx]);
+        }
+        fprintf(fp, "\n");
+    }
+    fclose(fp);
+}
+
+/* ---------------------------------------------------------------- additive */
+
+int ns_spectral_backend_select_device(NSSpectralData *d, int device) {
+    Backend *b = backend_of(d);
+    if (!b || b->ctx) return -1;
+    b->device = device;
+    return 0;
+}
+
+void ns_spectral_set_sync_policy(NSSpectralData *d, NSSyncPolicy policy) {
+    Backend *b = backend_of(d);
+    if (!b) return;
+    if (b->ctx && b->policy == NS_SYNC_EAGER && policy == NS_SYNC_LAZY) {
+        /* the device copy becomes the truth: seed it from the host arrays */
+        upload(d, NSB_OMEGA_HAT, d->omega_hat, "ns_spectral_set_sync_policy");
+        push_sfd_if_needed(d, "ns_spectral_set_sync_policy");
+        NSB_OK(nsb_set_time(b->ctx, d->t), "ns_spectral_set_sync_policy");
+    } else if (b->ctx && b->policy == NS_SYNC_LAZY && policy == NS_SYNC_EAGER) {
+        ns_spectral_sync_to_host(d, NS_FIELD_ALL);
+    }
+    b->policy = policy;
+}
+
+NSSyncPolicy ns_spectral_get_sync_policy(const NSSpectralData *d) {
+    const Backend *b = backend_of(d);
+    return b ? b->policy : NS_SYNC_EAGER;
+}
+
+int ns_spectral_sync_to_host(NSSpectralData *d, unsigned mask) {
+    static const char *W = "ns_spectral_sync_to_host";
+    nsb_ctx *c = ctx_of(d, W);
+    if (mask & NS_FIELD_OMEGA_HAT) download(d, NSB_OMEGA_HAT, d->omega_hat, W);
+    if (mask & NS_FIELD_SFD_HAT) {
+        const NSSpectralHyperviscosityConfig *h = &d->hyperviscosity;
+        if (h->sfd_enabled && h->sfd_strength > 0.0) download(d, NSB_SFD_HAT, d->sfd_hat, W);
+    }
+    if (mask & NS_FIELD_DERIVED) {
+        NSB_OK(nsb_compute_derivatives(c), W);
+        if (mask & NS_FIELD_PSI_HAT) download(d, NSB_PSI_HAT, d->psi_hat, W);
+        if (mask & NS_FIELD_U_HAT) download(d, NSB_U_HAT, d->u_hat, W);
+        if (mask & NS_FIELD_V_HAT) download(d, NSB_V_HAT, d->v_hat, W);
+        if (mask & NS_FIELD_U) download(d, NSB_U, d->u, W);
+        if (mask & NS_FIELD_V) download(d, NSB_V, d->v, W);
+        if (mask & NS_FIELD_OMEGA) download(d, NSB_OMEGA, d->omega, W);
+    }
+    if (mask & NS_FIELD_PSI) {
+        if (!(mask & NS_FIELD_DERIVED)) NSB_OK(nsb_velocity_from_vorticity(c), W);
+        const int src = NSB_PSI_HAT, dst = NSB_PSI;
+        NSB_OK(nsb_spectral_to_physical(c, 1, &src, &dst), W);
+        download(d, NSB_PSI, d->psi, W);
+    }
+    double dt;
+    int steps;
+    NSB_OK(nsb_get_state(c, &dt, &d->t, &steps), W);
+    return 0;
+}
+
+int ns_spectral_sync_to_device(NSSpectralData *d, unsigned mask) {
+    static const char *W = "ns_spectral_sync_to_device";
+    nsb_ctx *c = ctx_of(d, W);
+    if (mask & NS_FIELD_OMEGA_HAT) upload(d, NSB_OMEGA_HAT, d->omega_hat, W);
+    if (mask & NS_FIELD_SFD_HAT) upload(d, NSB_SFD_HAT, d->sfd_hat, W);
+    if (mask & NS_FIELD_PSI_HAT) upload(d, NSB_PSI_HAT, d->psi_hat, W);
+    NSB_OK(nsb_set_time(c, d->t), W);
+    return 0;
+}
+
+void *ns_spectral_backend_context(NSSpectralData *d) {
+    Backend *b = backend_of(d);
+    return b ? (void *)b->ctx : NULL;
+}
