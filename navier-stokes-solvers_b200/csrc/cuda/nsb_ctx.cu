@@ -66,6 +66,7 @@ struct nsb_ctx {
     int force_slot;
     int masked_nonzero;
     int has_beta;
+    int fast; /* warp-FFT fast paths enabled (NSB_DISABLE_FAST=1 forces the generic kernels) */
     long long launches;
     std::set<const void *> *smem_set;
     cudaEvent_t ev0, ev1;
@@ -197,6 +198,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     g.fsH = (size_t)g.ny * g.X1 * g.PH;
     g.norm = 1.0 / ((double)g.nx * (double)g.ny);
     c->has_beta = (g.Y2 > 1 || g.X1 > 1);
+    c->fast = !(getenv("NSB_DISABLE_FAST") && atoi(getenv("NSB_DISABLE_FAST")));
     c->buf_elems = 4 * (g.fsT > g.fsH ? g.fsT : g.fsH);
 
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -540,8 +542,27 @@ static int launch_beta(nsb_ctx *c, bool inverse, const BetaArgs &a) {
     return fail("unsupported Y2=%d", c->g.Y2);
 }
 
+#define NSB_G1024_WARPS 4
+
 static int launch_gamma(nsb_ctx *c, int mode, const GammaArgs &a) {
     const NsbGeom &g = c->g;
+    if (mode == NSB_GAMMA_STEP && g.X2 == 1024 && c->fast) {
+        GammaFastArgs fa;
+        fa.in = a.in; fa.out = a.out; fa.nvalid_in = a.nvalid_in; fa.nvalid_out = a.nvalid_out;
+        fa.umax_bits = a.umax_bits;
+        fa.npairs = (int)((size_t)g.ny * g.X1 / 2);
+        int blocks = (fa.npairs + NSB_G1024_WARPS - 1) / NSB_G1024_WARPS;
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        const size_t smem = NSB_G1024_SMEM(NSB_G1024_WARPS);
+        auto k = k_gamma1024<NSB_G1024_WARPS>;
+        if (ensure_smem(c, k, smem)) return -1;
+        prof_pre(c, PK_GAMMA);
+        NSB_LAUNCH(k, dim3(blocks), dim3(NSB_G1024_WARPS * 32), smem, c->stream, g, fa);
+        prof_post(c);
+        CKL();
+        c->launches++;
+        return 0;
+    }
     const dim3 grid((unsigned)((size_t)g.ny * g.X1 / 2)), block(256);
     const size_t smem = (size_t)4 * (g.X2 + 1) * sizeof(cd) + 256 * sizeof(double);
 #define NSB_GM(MODE)                                                     \

@@ -29,6 +29,7 @@
 #define NSB_KERNELS_CUH
 
 #include "nsb_fft.cuh"
+#include "nsb_fft1024.cuh"
 
 struct NsbGeom {
     int nx, ny, nkx;
@@ -711,6 +712,136 @@ __global__ void k_step_end(NsbScalars *sc) {
     sc->t = __dadd_rn(sc->t, sc->dt);
     sc->dt_hist[sc->step & 255] = sc->dt;
     sc->step += 1;
+}
+
+/* ------------------------------------------------- gamma, X2 == 1024 fast path */
+
+struct GammaFastArgs {
+    const cd *in;   /* H, 4 fields */
+    cd *out;        /* H' */
+    int nvalid_in, nvalid_out;
+    unsigned long long *umax_bits;
+    int npairs;
+};
+
+/* per-warp shared memory: transpose buffer | parked z1 (complex) | parked J of comb 0 |
+ * TMA landing buffer (two spectrum rows of 513) | mbarrier */
+#define NSB_G1024_T_BYTES (32 * NSB_TP * 8)
+#define NSB_G1024_L_BYTES (2 * 513 * 16)
+#define NSB_G1024_WARP_BYTES (NSB_G1024_T_BYTES + 1024 * 16 + 1024 * 8 + NSB_G1024_L_BYTES + 16)
+#define NSB_G1024_SMEM(warps) (1024 * 16 + (warps) * NSB_G1024_WARP_BYTES)
+
+/* Z[k] = A[k] + i B[k] for k <= 512, Z[k] = conj(A[1024-k]) + i conj(B[1024-k]) above;
+ * Im of the DC and Nyquist bins dropped (FFTW c2r convention). Lane t gets k = t + 32 m.
+ * A, B: the two spectrum rows in the shared-memory landing buffer (zero beyond nvalid). */
+__device__ __forceinline__ void nsb_load_hermitian1024(cd (&x)[32], const cd *A, const cd *B, int nvalid, int lane) {
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+        const int k = lane + 32 * m;
+        const bool lower = (m < 16) || (m == 16 && lane == 0);
+        const int kk = lower ? k : 1024 - k;
+        cd av = cmk(0.0, 0.0), bv = cmk(0.0, 0.0);
+        if (kk < nvalid) {
+            av = A[kk];
+            bv = B[kk];
+        }
+        if (k == 0 || k == 512) x[m] = cmk(av.x, bv.x);
+        else if (lower) x[m] = cmk(av.x - bv.y, av.y + bv.x);
+        else x[m] = cmk(av.x + bv.y, bv.x - av.y);
+    }
+}
+
+/*
+ * gamma for X2 == 1024: one WARP per comb pair, no block barrier after the twiddle
+ * table is staged. Per pair: 4 inverse + 1 forward warp FFT-1024, Jacobian and max|u|^2
+ * in registers. The two spectrum rows of the NEXT transform are fetched by TMA bulk copies
+ * (cp.async.bulk -> mbarrier) into the warp's landing buffer while the current transform
+ * runs, so global latency is off the critical path with one warp per scheduler.
+ * Same inputs/outputs as k_gamma<NSB_GAMMA_STEP>.
+ */
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_gamma1024(NsbGeom g, GammaFastArgs a) {
+    NSB_DYN_SMEM(unsigned char, raw);
+    cd *TW = reinterpret_cast<cd *>(raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wb = raw + 1024 * 16 + (size_t)warp * NSB_G1024_WARP_BYTES;
+    double *T = reinterpret_cast<double *>(wb);
+    cd *P = reinterpret_cast<cd *>(wb + NSB_G1024_T_BYTES);
+    double *PJ = reinterpret_cast<double *>(wb + NSB_G1024_T_BYTES + 1024 * 16);
+    cd *L = reinterpret_cast<cd *>(wb + NSB_G1024_T_BYTES + 1024 * 16 + 1024 * 8);
+    nsb_mbar_t *bar = reinterpret_cast<nsb_mbar_t *>(wb + NSB_G1024_T_BYTES + 1024 * 16 + 1024 * 8 + NSB_G1024_L_BYTES);
+    nsb_fill_tw1024(TW, g.WX, g.nx / 1024);
+    if (lane == 0) nsb_mbar_init(bar, 1);
+    __syncthreads();
+    const unsigned row_bytes = (unsigned)a.nvalid_in * 16u;
+    const int stride = gridDim.x * WARPS;
+    const int pair0 = blockIdx.x * WARPS + warp;
+    /* job = (pair, comb, pp): rows of fields 2pp, 2pp+1 of comb row 2*pair+comb */
+    auto issue = [&](int pair, int comb, int pp) {
+        if (lane == 0) {
+            const size_t row = (size_t)(2 * pair + comb) * g.PH;
+            nsb_fence_proxy_async();
+            nsb_mbar_expect_tx(bar, 2u * row_bytes);
+            nsb_bulk_g2s(L, a.in + (size_t)(2 * pp) * g.fsH + row, row_bytes, bar);
+            nsb_bulk_g2s(L + 513, a.in + (size_t)(2 * pp + 1) * g.fsH + row, row_bytes, bar);
+        }
+    };
+    unsigned phase = 0;
+    if (pair0 < a.npairs) issue(pair0, 0, 0);
+    double umax = 0.0;
+    for (int pair = pair0; pair < a.npairs; pair += stride) {
+        cd x[32];
+#pragma unroll 1
+        for (int comb = 0; comb < 2; ++comb) {
+            nsb_mbar_wait(bar, phase);
+            phase ^= 1u;
+            nsb_load_hermitian1024(x, L, L + 513, a.nvalid_in, lane);
+#ifdef NSB_DEBUG_G
+            if (lane == 1 && pair == 0) { const cd *A0 = a.in + (size_t)(2*pair+comb)*g.PH; printf("comb %d L[1]=(%g,%g) A[1]=(%g,%g) B: L=(%g,%g) g=(%g,%g) x0=(%g,%g)\n", comb, L[1].x, L[1].y, A0[1].x, A0[1].y, L[514].x, L[514].y, (A0+g.fsH)[1].x, (A0+g.fsH)[1].y, x[0].x, x[0].y); }
+#endif
+            __syncwarp();
+            issue(pair, comb, 1);
+            nsb_fft1024_warp<true>(x, T, TW, lane);
+#pragma unroll
+            for (int m = 0; m < 32; ++m) P[m * 32 + lane] = x[m];
+            nsb_mbar_wait(bar, phase);
+            phase ^= 1u;
+            nsb_load_hermitian1024(x, L, L + 513, a.nvalid_in, lane);
+            __syncwarp();
+            if (comb == 0) issue(pair, 1, 0);
+            else if (pair + stride < a.npairs) issue(pair + stride, 0, 0);
+            nsb_fft1024_warp<true>(x, T, TW, lane);
+#pragma unroll
+            for (int m = 0; m < 32; ++m) {
+                const cd z1 = P[m * 32 + lane], z2 = x[m];
+                /* spectral_core.c:103 and spectral_time_integration.c:16 */
+                const double J = __dsub_rn(__dmul_rn(z1.x, z2.y), __dmul_rn(z1.y, z2.x));
+                umax = fmax(umax, __dadd_rn(__dmul_rn(z1.y, z1.y), __dmul_rn(z1.x, z1.x)));
+                if (comb == 0) PJ[m * 32 + lane] = J;
+                else x[m] = cmk(PJ[m * 32 + lane], J);
+            }
+        }
+        nsb_fft1024_warp<false>(x, T, TW, lane);
+#pragma unroll
+        for (int m = 0; m < 32; ++m) P[m * 32 + lane] = x[m]; /* natural order: index k = lane + 32 m */
+        __syncwarp();
+        cd *o0 = a.out + (size_t)(2 * pair) * g.PH, *o1 = o0 + g.PH;
+#pragma unroll
+        for (int m = 0; m <= 16; ++m) {
+            const int k = lane + 32 * m;
+            if (k <= 512 && k < a.nvalid_out) {
+                const cd Pk = P[k], Q = P[(1024 - k) & 1023];
+                o0[k] = cmk(0.5 * (Pk.x + Q.x), 0.5 * (Pk.y - Q.y));
+                o1[k] = cmk(0.5 * (Pk.y + Q.y), -0.5 * (Pk.x - Q.x));
+            }
+        }
+        __syncwarp();
+    }
+    if (a.umax_bits != nullptr) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, off));
+        if (lane == 0) atomicMax(a.umax_bits, (unsigned long long)__double_as_longlong(umax));
+    }
 }
 
 #endif

@@ -22,4 +22,60 @@
 
 typedef double2 cd; /* complex double: x = re, y = im */
 
+/*
+ * TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers. global -> shared,
+ * completion counted in bytes on an mbarrier in shared memory. Addresses and sizes must be
+ * multiples of 16 bytes. Under the CPU emulator the copy is an immediate memcpy.
+ */
+#ifdef NSB_EMULATE
+typedef unsigned long long nsb_mbar_t;
+/* emulated mbarrier: low 32 bits = completed phases, high 32 bits = pending tx bytes */
+static inline void nsb_mbar_init(nsb_mbar_t *bar, int) { *bar = 0; }
+static inline void nsb_mbar_expect_tx(nsb_mbar_t *bar, unsigned bytes) { *bar += (unsigned long long)bytes << 32; }
+static inline void nsb_bulk_g2s(void *dst, const void *src, unsigned bytes, nsb_mbar_t *bar) {
+    memcpy(dst, src, bytes);
+    *bar -= (unsigned long long)bytes << 32;
+    if ((*bar >> 32) == 0) *bar += 1;
+}
+static inline void nsb_mbar_wait(nsb_mbar_t *bar, unsigned parity) {
+    while (((unsigned)(*bar) & 1u) == parity) nsbemu::yield();
+}
+static inline void nsb_fence_proxy_async() {}
+#else
+typedef unsigned long long nsb_mbar_t;
+__device__ __forceinline__ unsigned nsb_smem_addr(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void nsb_mbar_init(nsb_mbar_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nsb_smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void nsb_mbar_expect_tx(nsb_mbar_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nsb_smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void nsb_bulk_g2s(void *dst, const void *src, unsigned bytes, nsb_mbar_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     nsb_smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(nsb_smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void nsb_mbar_wait(nsb_mbar_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "NSB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra NSB_DONE_%=;\n"
+        "bra NSB_WAIT_%=;\n"
+        "NSB_DONE_%=:\n"
+        "}\n" ::"r"(nsb_smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void nsb_fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+#endif
+
 #endif

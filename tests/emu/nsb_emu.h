@@ -47,6 +47,7 @@ struct Fiber {
     char *stack;
     uint3_emu tid;
     bool done;
+    int warp, lane;
 };
 struct State {
     uint3_emu bid;
@@ -55,10 +56,19 @@ struct State {
     Fiber *cur;
     ucontext_t sched;
     std::function<void()> *body;
+    /* barrier bookkeeping: arrivals are counted, exited threads drop out */
+    int live, block_arrived;
+    unsigned block_gen;
+    std::vector<int> warp_live, warp_arrived;
+    std::vector<unsigned> warp_gen;
+    std::vector<double> warp_buf;
 };
 extern State g;
 void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> body);
 void barrier();
+void warp_barrier();
+void yield();
+double shfl(double v, int src_lane);
 }  // namespace nsbemu
 
 #define threadIdx (nsbemu::g.cur->tid)
@@ -66,6 +76,11 @@ void barrier();
 #define blockDim (nsbemu::g.bdim)
 #define gridDim (nsbemu::g.gdim)
 #define __syncthreads() nsbemu::barrier()
+#define __syncwarp() nsbemu::warp_barrier()
+static inline double __shfl_xor_sync(unsigned, double v, int lane_mask) {
+    return nsbemu::shfl(v, nsbemu::g.cur->lane ^ lane_mask);
+}
+static inline double __shfl_sync(unsigned, double v, int src_lane) { return nsbemu::shfl(v, src_lane); }
 #define NSB_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(nsbemu::g.smem)
 
 template <class T> static inline T __ldg(const T *p) { return *p; }

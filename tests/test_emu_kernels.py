@@ -50,3 +50,10 @@ def test_emu_step_forced_colored_sfd_split(nsb, emu_lib, oracles):
 
 def test_emu_free_running(nsb, emu_lib, oracles):
     pc.check_free_running(nsb, emu_lib, oracles, best_oracle_kind(oracles), 32, 32, 20, every=5, hv=HV)
+
+
+@pytest.mark.parametrize("nx,ny,plan", [(1024, 16, {}), (2048, 16, dict(x2=1024))])
+def test_emu_gamma1024_fast_path(nsb, emu_lib, oracles, nx, ny, plan):
+    """X2 == 1024 selects the warp-level register FFT kernel (k_gamma1024)."""
+    pc.check_per_step(nsb, emu_lib, oracles, best_oracle_kind(oracles), nx, ny, 2, hv=HV,
+                      forcing=dict(kind="white"), **plan)
