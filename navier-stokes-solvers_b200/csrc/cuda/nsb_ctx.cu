@@ -51,7 +51,7 @@ struct nsb_ctx {
     void *fields[NSB_NUM_FIELDS];
     cd *bufA, *bufB;
     size_t buf_elems;
-    double *d_kx, *d_ky;
+    double *d_kx, *d_ky, *d_kyK;
     cd *d_WY, *d_WX;
     NsbScalars *d_sc;
     NsbScalars *h_sc; /* pinned */
@@ -67,6 +67,9 @@ struct nsb_ctx {
     int masked_nonzero;
     int has_beta;
     int fast; /* warp-FFT fast paths enabled (NSB_DISABLE_FAST=1 forces the generic kernels) */
+    /* K-layout copies of the RK state used by the fused column kernel (k_alpha1024) */
+    cd *kW0, *kWst, *kACC, *kSFD;
+    int k_truth; /* 1: kW0 (and kSFD) hold the current state, the reference-layout fields are stale */
     long long launches;
     std::set<const void *> *smem_set;
     cudaEvent_t ev0, ev1;
@@ -199,6 +202,8 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     g.norm = 1.0 / ((double)g.nx * (double)g.ny);
     c->has_beta = (g.Y2 > 1 || g.X1 > 1);
     c->fast = !(getenv("NSB_DISABLE_FAST") && atoi(getenv("NSB_DISABLE_FAST")));
+    c->kW0 = c->kWst = c->kACC = c->kSFD = nullptr;
+    c->k_truth = 0;
     c->buf_elems = 4 * (g.fsT > g.fsH ? g.fsT : g.fsH);
 
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -215,6 +220,13 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     CK(cudaMalloc((void **)&c->d_ky, ky.size() * sizeof(double)));
     CK(cudaMemcpy(c->d_kx, kx.data(), kx.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_ky, ky.data(), ky.size() * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        std::vector<double> kyK(g.ny);
+        for (int j2 = 0; j2 < g.Y2; ++j2)
+            for (int j1 = 0; j1 < g.Y1; ++j1) kyK[(size_t)j2 * g.Y1 + j1] = ky[(size_t)j1 * g.Y2 + j2];
+        CK(cudaMalloc((void **)&c->d_kyK, kyK.size() * sizeof(double)));
+        CK(cudaMemcpy(c->d_kyK, kyK.data(), kyK.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     std::vector<cd> w;
     fill_twiddles(w, g.ny);
     CK(cudaMalloc((void **)&c->d_WY, w.size() * sizeof(cd)));
@@ -222,7 +234,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     fill_twiddles(w, g.nx);
     CK(cudaMalloc((void **)&c->d_WX, w.size() * sizeof(cd)));
     CK(cudaMemcpy(c->d_WX, w.data(), w.size() * sizeof(cd), cudaMemcpyHostToDevice));
-    g.kx = c->d_kx; g.ky = c->d_ky; g.WY = c->d_WY; g.WX = c->d_WX;
+    g.kx = c->d_kx; g.ky = c->d_ky; g.kyK = c->d_kyK; g.WY = c->d_WY; g.WX = c->d_WX;
 
     CK(cudaMalloc((void **)&c->d_sc, sizeof(NsbScalars)));
     CK(cudaMemset(c->d_sc, 0, sizeof(NsbScalars)));
@@ -254,7 +266,11 @@ extern "C" void nsb_ctx_destroy(nsb_ctx *c) {
     cudaStreamSynchronize(c->stream);
     for (int f = 0; f < NSB_NUM_FIELDS; ++f) if (c->fields[f]) cudaFree(c->fields[f]);
     cudaFree(c->bufA); cudaFree(c->bufB);
-    cudaFree(c->d_kx); cudaFree(c->d_ky); cudaFree(c->d_WY); cudaFree(c->d_WX);
+    if (c->kW0) cudaFree(c->kW0);
+    if (c->kWst) cudaFree(c->kWst);
+    if (c->kACC) cudaFree(c->kACC);
+    if (c->kSFD) cudaFree(c->kSFD);
+    cudaFree(c->d_kx); cudaFree(c->d_ky); cudaFree(c->d_kyK); cudaFree(c->d_WY); cudaFree(c->d_WX);
     cudaFree(c->d_sc); cudaFreeHost(c->h_sc);
     if (c->d_force) cudaFree(c->d_force);
     for (int s = 0; s < NSB_FORCE_RING; ++s) {
@@ -330,6 +346,62 @@ static int pointwise_grid(nsb_ctx *c) {
     return (int)blocks;
 }
 
+static bool alpha_fast_ok(const nsb_ctx *c) { return c->fast && c->g.Y1 == 1024 && !c->masked_nonzero; }
+
+static int klayout_copy(nsb_ctx *c, bool to_k, cd *ref, cd *K) {
+    const NsbGeom &g = c->g;
+    const dim3 grid((g.ncol + 31) / 32, g.Y1 / 32, g.Y2), block(32, 8);
+    if (to_k) {
+        auto k = k_ref_to_klayout;
+        NSB_LAUNCH(k, grid, block, 0, c->stream, g, (const cd *)ref, K);
+    } else {
+        auto k = k_klayout_to_ref;
+        NSB_LAUNCH(k, grid, block, 0, c->stream, g, (const cd *)K, ref);
+    }
+    CKL();
+    c->launches++;
+    return 0;
+}
+
+/* make the reference-layout OMEGA_HAT / SFD_HAT current again (after fast-path steps) */
+static int sync_ref(nsb_ctx *c) {
+    if (!c->k_truth) return 0;
+    void *w;
+    if (get_field(c, NSB_OMEGA_HAT, &w)) return -1;
+    if (klayout_copy(c, false, (cd *)w, c->kW0)) return -1;
+    if (c->hv.sfd && c->kSFD) {
+        void *s;
+        if (get_field(c, NSB_SFD_HAT, &s)) return -1;
+        if (klayout_copy(c, false, (cd *)s, c->kSFD)) return -1;
+    }
+    c->k_truth = 0;
+    return 0;
+}
+
+/* make the K-layout state current (before fast-path steps) */
+static int sync_k(nsb_ctx *c) {
+    const size_t bytes = (size_t)c->g.ncol * c->g.ny * sizeof(cd);
+    if (!c->kW0) {
+        CK(cudaMalloc((void **)&c->kW0, bytes));
+        CK(cudaMalloc((void **)&c->kWst, bytes));
+        CK(cudaMalloc((void **)&c->kACC, bytes));
+        CK(cudaMemsetAsync(c->kWst, 0, bytes, c->stream));
+        CK(cudaMemsetAsync(c->kACC, 0, bytes, c->stream));
+    }
+    if (c->hv.sfd && !c->kSFD) CK(cudaMalloc((void **)&c->kSFD, bytes));
+    if (c->k_truth) return 0;
+    void *w;
+    if (get_field(c, NSB_OMEGA_HAT, &w)) return -1;
+    if (klayout_copy(c, true, (cd *)w, c->kW0)) return -1;
+    if (c->hv.sfd) {
+        void *s;
+        if (get_field(c, NSB_SFD_HAT, &s)) return -1;
+        if (klayout_copy(c, true, (cd *)s, c->kSFD)) return -1;
+    }
+    c->k_truth = 1;
+    return 0;
+}
+
 static int scan_masked(nsb_ctx *c) {
     void *w;
     if (get_field(c, NSB_OMEGA_HAT, &w)) return -1;
@@ -348,6 +420,7 @@ static int scan_masked(nsb_ctx *c) {
 extern "C" int nsb_upload(nsb_ctx *c, int field, const void *host) {
     if (!c || !host) return fail("nsb_upload: null argument");
     CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     void *d;
     if (get_field(c, field, &d)) return -1;
     const size_t bytes = field_is_phys(field) ? c->N * sizeof(double) : c->M * sizeof(cd);
@@ -360,6 +433,7 @@ extern "C" int nsb_upload(nsb_ctx *c, int field, const void *host) {
 extern "C" int nsb_download(nsb_ctx *c, int field, void *host) {
     if (!c || !host) return fail("nsb_download: null argument");
     CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     void *d;
     if (get_field(c, field, &d)) return -1;
     const size_t bytes = field_is_phys(field) ? c->N * sizeof(double) : c->M * sizeof(cd);
@@ -371,6 +445,7 @@ extern "C" int nsb_download(nsb_ctx *c, int field, void *host) {
 extern "C" int nsb_zero(nsb_ctx *c, int field) {
     if (!c) return fail("null context");
     CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     void *d;
     if (get_field(c, field, &d)) return -1;
     const size_t bytes = field_is_phys(field) ? c->N * sizeof(double) : c->M * sizeof(cd);
@@ -383,6 +458,7 @@ extern "C" int nsb_copy(nsb_ctx *c, int dst, int src) {
     if (!c) return fail("null context");
     if (field_is_phys(dst) != field_is_phys(src)) return fail("nsb_copy: field kinds differ");
     CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     void *d, *s;
     if (get_field(c, dst, &d) || get_field(c, src, &s)) return -1;
     const size_t bytes = field_is_phys(dst) ? c->N * sizeof(double) : c->M * sizeof(cd);
@@ -401,6 +477,8 @@ extern "C" int nsb_set_hyperviscosity(nsb_ctx *c, const nsb_hyperviscosity *h) {
     c->hv.inv_bw = h->inv_bandwidth;
     c->hv.sfd_strength = h->sfd_strength;
     c->hv.sfd_timescale = h->sfd_timescale;
+    CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     if (c->hv.sfd) {
         void *tmp;
         CK(cudaSetDevice(c->device));
@@ -542,6 +620,30 @@ static int launch_beta(nsb_ctx *c, bool inverse, const BetaArgs &a) {
     return fail("unsupported Y2=%d", c->g.Y2);
 }
 
+static int launch_alpha1024(nsb_ctx *c, bool fwd, bool inv, const AlphaFastArgs &a) {
+    const NsbGeom &g = c->g;
+    const dim3 grid((g.ncol + NSB_A1024_COLS - 1) / NSB_A1024_COLS, g.Y2), block(128);
+    const size_t smem = NSB_A1024_SMEM;
+    prof_pre(c, fwd ? PK_ALPHA_FWD : PK_ALPHA_INV);
+    if (fwd && inv) {
+        auto k = k_alpha1024<true, true>;
+        if (ensure_smem(c, k, smem)) return -1;
+        NSB_LAUNCH(k, grid, block, smem, c->stream, g, a);
+    } else if (fwd) {
+        auto k = k_alpha1024<true, false>;
+        if (ensure_smem(c, k, smem)) return -1;
+        NSB_LAUNCH(k, grid, block, smem, c->stream, g, a);
+    } else {
+        auto k = k_alpha1024<false, true>;
+        if (ensure_smem(c, k, smem)) return -1;
+        NSB_LAUNCH(k, grid, block, smem, c->stream, g, a);
+    }
+    prof_post(c);
+    CKL();
+    c->launches++;
+    return 0;
+}
+
 #define NSB_G1024_WARPS 4
 
 static int launch_gamma(nsb_ctx *c, int mode, const GammaArgs &a) {
@@ -660,6 +762,7 @@ extern "C" int nsb_physical_to_spectral(nsb_ctx *c, int src_phys, int dst_hat) {
     if (!c) return fail("null context");
     if (!field_is_phys(src_phys) || !field_is_hat(dst_hat)) return fail("nsb_physical_to_spectral: bad fields");
     CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     void *src, *dst;
     if (get_field(c, src_phys, &src) || get_field(c, dst_hat, &dst)) return -1;
     const NsbGeom &g = c->g;
@@ -682,6 +785,7 @@ extern "C" int nsb_spectral_to_physical(nsb_ctx *c, int nf, const int *src_hat, 
     if (!c || !src_hat || !dst_phys) return fail("nsb_spectral_to_physical: null argument");
     if (nf < 1 || nf > 4) return fail("nsb_spectral_to_physical: nf must be 1..4");
     CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     const cd *src[4] = {nullptr, nullptr, nullptr, nullptr};
     double *dst[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int f = 0; f < nf; ++f) {
@@ -697,6 +801,7 @@ extern "C" int nsb_apply_dealiasing(nsb_ctx *c, int field_hat) {
     if (!c) return fail("null context");
     if (!field_is_hat(field_hat)) return fail("nsb_apply_dealiasing: bad field");
     CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     void *f;
     if (get_field(c, field_hat, &f)) return -1;
     auto k = k_apply_dealiasing;
@@ -710,6 +815,7 @@ extern "C" int nsb_apply_dealiasing(nsb_ctx *c, int field_hat) {
 extern "C" int nsb_velocity_from_vorticity(nsb_ctx *c) {
     if (!c) return fail("null context");
     CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     void *w, *psi, *uh, *vh;
     if (get_field(c, NSB_OMEGA_HAT, &w) || get_field(c, NSB_PSI_HAT, &psi) || get_field(c, NSB_U_HAT, &uh) ||
         get_field(c, NSB_V_HAT, &vh))
@@ -735,6 +841,7 @@ extern "C" int nsb_compute_derivatives(nsb_ctx *c) {
 extern "C" int nsb_nonlinear_terms(nsb_ctx *c) {
     if (!c) return fail("null context");
     CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     void *psi, *w, *nl;
     if (get_field(c, NSB_PSI_HAT, &psi) || get_field(c, NSB_OMEGA_HAT, &w) || get_field(c, NSB_NONLINEAR_HAT, &nl))
         return -1;
@@ -750,6 +857,7 @@ extern "C" int nsb_hyperviscosity_apply(nsb_ctx *c, int rhs_hat, int state_hat) 
     if (!field_is_hat(rhs_hat) || !field_is_hat(state_hat)) return fail("nsb_hyperviscosity_apply: bad fields");
     if (!c->hv.visc && !c->hv.sfd) return 0; /* hyperviscosity.c:120-122 */
     CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     void *rhs, *st, *sfd = nullptr;
     if (get_field(c, rhs_hat, &rhs) || get_field(c, state_hat, &st)) return -1;
     if (c->hv.sfd && get_field(c, NSB_SFD_HAT, &sfd)) return -1;
@@ -765,6 +873,7 @@ extern "C" int nsb_hyperviscosity_post_step(nsb_ctx *c, int state_hat, double dt
     if (!field_is_hat(state_hat)) return fail("nsb_hyperviscosity_post_step: bad field");
     if (!(dt > 0.0) || !c->hv.sfd || !(c->hv.sfd_strength > 0.0) || !(c->hv.sfd_timescale > 0.0)) return 0;
     CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     void *st, *sfd;
     if (get_field(c, state_hat, &st) || get_field(c, NSB_SFD_HAT, &sfd)) return -1;
     double alpha = dt / c->hv.sfd_timescale;
@@ -812,6 +921,7 @@ extern "C" int nsb_cfl_timestep_uv(nsb_ctx *c, double *dt_out) {
 extern "C" int nsb_cfl_timestep(nsb_ctx *c, double *dt_out) {
     if (!c || !dt_out) return fail("nsb_cfl_timestep: null argument");
     CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     void *w;
     if (get_field(c, NSB_OMEGA_HAT, &w)) return -1;
     CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
@@ -831,6 +941,12 @@ extern "C" int nsb_rk4_step(nsb_ctx *c, double dt) {
         return -1;
     if (c->hv.sfd && get_field(c, NSB_SFD_HAT, &sfd)) return -1;
     const bool device_dt = !(dt > 0.0);
+    const bool afast = alpha_fast_ok(c);
+    if (afast) {
+        if (sync_k(c)) return -1;
+    } else if (sync_ref(c)) {
+        return -1;
+    }
     if (!device_dt) {
         auto k = k_set_dt;
         NSB_LAUNCH(k, dim3(1), dim3(32), 0, c->stream, c->d_sc, dt);
@@ -852,11 +968,21 @@ extern "C" int nsb_rk4_step(nsb_ctx *c, double dt) {
         /* the CFL kernel must sit between gamma (stage 1) and the first RK update */
         const bool want_umax = device_dt && stage == 1;
         const NsbGeom &g = c->g;
-        AlphaInvArgs ai;
-        memset(&ai, 0, sizeof(ai));
-        ai.nf = 4; ai.src[0] = src;
-        ai.out = c->bufA; ai.out_fs = g.fsT; ai.out_pitch = g.PT;
-        if (launch_alpha_inv(c, NSB_SRC_STEP, ai)) return -1;
+        if (afast) {
+            rk.W0 = c->kW0; rk.Wst = c->kWst; rk.ACC = c->kACC; rk.SFD = c->kSFD;
+            if (stage == 1) {
+                AlphaFastArgs fa;
+                memset(&fa, 0, sizeof(fa));
+                fa.out = c->bufA; fa.out_fs = g.fsT; fa.out_pitch = g.PT; fa.Wsrc = c->kW0; fa.rk = rk;
+                if (launch_alpha1024(c, false, true, fa)) return -1;
+            }
+        } else {
+            AlphaInvArgs ai;
+            memset(&ai, 0, sizeof(ai));
+            ai.nf = 4; ai.src[0] = src;
+            ai.out = c->bufA; ai.out_fs = g.fsT; ai.out_pitch = g.PT;
+            if (launch_alpha_inv(c, NSB_SRC_STEP, ai)) return -1;
+        }
         const cd *H = c->bufA;
         cd *Hp = c->bufB;
         if (c->has_beta) {
@@ -872,6 +998,22 @@ extern "C" int nsb_rk4_step(nsb_ctx *c, double dt) {
         ga.umax_bits = want_umax ? &c->d_sc->umax_bits : nullptr;
         if (launch_gamma(c, NSB_GAMMA_STEP, ga)) return -1;
         if (want_umax && launch_cfl(c)) return -1;
+        if (afast) {
+            /* beta_fwd, then ONE kernel: forward column FFTs + RK update of this stage +
+             * inverse column FFTs of the next stage */
+            const cd *Tp = Hp;
+            if (c->has_beta) {
+                BetaArgs b; b.in = Hp; b.out = c->bufB; b.nf = 1;
+                if (launch_beta(c, false, b)) return -1;
+                Tp = c->bufB;
+            }
+            AlphaFastArgs fa;
+            memset(&fa, 0, sizeof(fa));
+            fa.in = Tp; fa.in_pitch = g.PT;
+            fa.out = c->bufA; fa.out_fs = g.fsT; fa.out_pitch = g.PT; fa.rk = rk;
+            if (launch_alpha1024(c, true, stage < 4, fa)) return -1;
+            continue;
+        }
         if (forward_tail(c, Hp, NSB_EPI_RK, af)) return -1;
         if (c->masked_nonzero) {
             auto k = k_rk_masked;
@@ -890,6 +1032,7 @@ extern "C" int nsb_rk4_step(nsb_ctx *c, double dt) {
 extern "C" int nsb_diagnostics(nsb_ctx *c, double out[4]) {
     if (!c || !out) return fail("nsb_diagnostics: null argument");
     CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
     void *w;
     if (get_field(c, NSB_OMEGA_HAT, &w)) return -1;
     CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));

@@ -40,6 +40,7 @@ struct NsbGeom {
     int BC;          /* k2 values per beta CTA */
     size_t fsT, fsH; /* field strides (complex elements) */
     const double *kx, *ky;
+    const double *kyK; /* ky permuted for the fast column kernel: kyK[j2*Y1 + j1] = ky[j1*Y2 + j2] */
     const cd *WY, *WX; /* exp(-2 pi i m/ny), exp(-2 pi i m/nx) */
     double norm;       /* 1/(nx*ny) */
 };
@@ -112,8 +113,8 @@ __device__ __forceinline__ cd nsb_damping(const NsbHv &h, double k2, cd W, const
  * Explicit _rn intrinsics keep nvcc from contracting into FMAs so the pointwise
  * arithmetic rounds like the -ffp-contract=off oracle.
  */
-__device__ __forceinline__ void nsb_rk_update(const NsbRk &r, size_t idx, double kxv, double kyv, int i,
-                                              int band, cd Nh) {
+__device__ __forceinline__ cd nsb_rk_update(const NsbRk &r, size_t idx, double kxv, double kyv, int i,
+                                            int band, cd Nh) {
     const cd W0v = r.W0[idx];
     const cd W = (r.stage == 1) ? W0v : r.Wst[idx];
     const double k2 = __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv));
@@ -134,12 +135,16 @@ __device__ __forceinline__ void nsb_rk_update(const NsbRk &r, size_t idx, double
     if (r.stage == 1) {
         r.ACC[idx] = k;
         const double c = __dmul_rn(0.5, dt);
-        r.Wst[idx] = cmk(__dadd_rn(W0v.x, __dmul_rn(c, k.x)), __dadd_rn(W0v.y, __dmul_rn(c, k.y)));
+        const cd Wn = cmk(__dadd_rn(W0v.x, __dmul_rn(c, k.x)), __dadd_rn(W0v.y, __dmul_rn(c, k.y)));
+        r.Wst[idx] = Wn;
+        return Wn;
     } else if (r.stage == 2 || r.stage == 3) {
         const cd a = r.ACC[idx];
         r.ACC[idx] = cmk(__dadd_rn(a.x, __dmul_rn(2.0, k.x)), __dadd_rn(a.y, __dmul_rn(2.0, k.y)));
         const double c = (r.stage == 2) ? __dmul_rn(0.5, dt) : dt;
-        r.Wst[idx] = cmk(__dadd_rn(W0v.x, __dmul_rn(c, k.x)), __dadd_rn(W0v.y, __dmul_rn(c, k.y)));
+        const cd Wn = cmk(__dadd_rn(W0v.x, __dmul_rn(c, k.x)), __dadd_rn(W0v.y, __dmul_rn(c, k.y)));
+        r.Wst[idx] = Wn;
+        return Wn;
     } else {
         const cd a = r.ACC[idx];
         const double c = __ddiv_rn(dt, 6.0);
@@ -154,6 +159,7 @@ __device__ __forceinline__ void nsb_rk_update(const NsbRk &r, size_t idx, double
             r.SFD[idx] = cmk(__dadd_rn(__dmul_rn(om, S.x), __dmul_rn(al, Wn.x)),
                              __dadd_rn(__dmul_rn(om, S.y), __dmul_rn(al, Wn.y)));
         }
+        return Wn;
     }
 }
 
@@ -841,6 +847,206 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gamma1024(NsbGeom g, GammaFas
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, off));
         if (lane == 0) atomicMax(a.umax_bits, (unsigned long long)__double_as_longlong(umax));
+    }
+}
+
+/* ------------------------------------------- alpha, Y1 == 1024 fused fast path */
+
+/*
+ * Internal "K layout" of the RK state arrays used by the fast path: retained columns
+ * only, K[(ic*Y2 + j2)*Y1 + j1] with j = j1*Y2 + j2, so that the 32 lanes of a warp that
+ * owns column ic touch 512 contiguous bytes. Converted from / to the reference layout
+ * (f_hat[j*nkx + i]) only at the API boundary (upload, download, diagnostics).
+ */
+__global__ void __launch_bounds__(256) k_ref_to_klayout(NsbGeom g, const cd *ref, cd *K) {
+    __shared__ cd tile[32][33];
+    /* grid: (ceil(ncol/32), Y1/32, Y2); block (32, 8) */
+    const int j2 = blockIdx.z, ic0 = blockIdx.x * 32, j10 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int j = (j10 + r) * g.Y2 + j2, ic = ic0 + threadIdx.x;
+        tile[r][threadIdx.x] = (ic < g.ncol) ? ref[(size_t)j * g.nkx + ic] : cmk(0.0, 0.0);
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int ic = ic0 + r;
+        if (ic < g.ncol) K[((size_t)ic * g.Y2 + j2) * g.Y1 + j10 + threadIdx.x] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_klayout_to_ref(NsbGeom g, const cd *K, cd *ref) {
+    __shared__ cd tile[32][33];
+    const int j2 = blockIdx.z, ic0 = blockIdx.x * 32, j10 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int ic = ic0 + r;
+        tile[r][threadIdx.x] = (ic < g.ncol) ? K[((size_t)ic * g.Y2 + j2) * g.Y1 + j10 + threadIdx.x] : cmk(0.0, 0.0);
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int j = (j10 + r) * g.Y2 + j2, ic = ic0 + threadIdx.x;
+        if (ic < g.ncol) ref[(size_t)j * g.nkx + ic] = tile[threadIdx.x][r];
+    }
+}
+
+struct AlphaFastArgs {
+    const cd *in;    /* T' (forward input) */
+    int in_pitch;
+    cd *out;         /* T, 4 fields (inverse output) */
+    size_t out_fs;
+    int out_pitch;
+    const cd *Wsrc;  /* K-layout state feeding the inverse part when there is no forward part */
+    NsbRk rk;        /* K-layout pointers */
+};
+
+#define NSB_A1024_COLS 4
+#define NSB_A1024_SMEM (1024 * 16 + 1024 * NSB_A1024_COLS * 16 + 32 * 16)
+
+/* shared tile S[1024 rows][4 columns], 16-byte chunks XOR-swizzled so that row-wise
+ * (cooperative, coalesced) and column-wise (per-warp FFT) accesses are both conflict free */
+__device__ __forceinline__ int nsb_sidx(int row, int c) { return row * NSB_A1024_COLS + (c ^ ((row >> 1) & 3)); }
+
+/* warp FFT-1024 whose transpose goes through the warp's own column of S (skewed so the
+ * strided read is conflict free as well) */
+template <bool INV>
+__device__ __forceinline__ void nsb_fft1024_warp_col(cd (&x)[32], cd *S, int col, const cd *TW, int lane) {
+    nsb_dft32<INV>(x);
+#pragma unroll
+    for (int r = 1; r < 32; ++r) {
+        const cd tw = TW[r * 32 + lane];
+        x[r] = INV ? cmulc(x[r], tw) : cmul(x[r], tw);
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r) S[nsb_sidx(32 * r + ((lane + r) & 31), col)] = x[r];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 32; ++q) x[q] = S[nsb_sidx(32 * lane + ((q + lane) & 31), col)];
+    __syncwarp();
+    nsb_dft32<INV>(x);
+}
+
+#ifdef NSB_EMULATE
+#define NSB_NOINLINE
+#else
+#define NSB_NOINLINE __noinline__
+#endif
+
+__device__ NSB_NOINLINE cd nsb_rk_update_call(const NsbRk *r, size_t idx, double kxv, double kyv, int i, int band,
+                                             cd Nh) {
+    return nsb_rk_update(*r, idx, kxv, kyv, i, band, Nh);
+}
+
+/*
+ * Fused column kernel for Y1 == 1024. CTA = 4 warps = 4 adjacent retained columns at one
+ * residue j2; during a transform a warp owns one column and holds its 1024 elements in
+ * registers. One transform body (the inverse; the forward one runs as conj o inverse o
+ * conj) is looped over up to five jobs:
+ *   job 0 (FWD)  T' tile -> cooperative coalesced load into swizzled smem -> y twiddle ->
+ *                forward warp FFT -> back to the tile; then ALL threads sweep the tile for
+ *                -1/(nx ny), mask, RHS + damping + forcing + RK stage update against the
+ *                K-layout state (512-byte coalesced, several loads in flight per thread)
+ *   jobs 1-4 (INV) next-stage state (K layout) -> psi, i k fields -> inverse warp FFT ->
+ *                y twiddle -> tile -> cooperative coalesced store to T[f]
+ * Replaces k_alpha_fwd<RK> of stage s followed by k_alpha_inv<STEP> of stage s+1.
+ */
+template <bool FWD, bool INV>
+__global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a) {
+    NSB_DYN_SMEM(cd, smem);
+    cd *TW = smem;
+    cd *S = smem + 1024;
+    cd *TB = S + 1024 * NSB_A1024_COLS; /* TB[m] = exp(-2 pi i (32 j2 m)/ny) */
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j2 = blockIdx.y, ic0 = blockIdx.x * NSB_A1024_COLS;
+    const int ic = ic0 + warp;
+    const bool active = ic < g.ncol;
+    const int cc = threadIdx.x & 3, rr = threadIdx.x >> 2; /* cooperative copies: 4 threads per row */
+    nsb_fill_tw1024(TW, g.WY, g.ny / 1024);
+    if (threadIdx.x < 32) TB[threadIdx.x] = __ldg(&g.WY[(size_t)32 * j2 * threadIdx.x]);
+    /* y twiddle exp(-2 pi i j2 y1/ny), y1 = lane + 32 m, factored as ta * TB[m] */
+    const cd ta = __ldg(&g.WY[(size_t)j2 * lane]);
+    const double *kyc = g.kyK + (size_t)j2 * 1024; /* ky of this CTA's rows, indexed by j1 */
+    const double kxv = active ? __ldg(&g.kx[ic]) : 0.0;
+    const size_t kbase = ((size_t)ic * g.Y2 + j2) * 1024;
+    const cd *Wre = FWD ? a.rk.Wst : a.Wsrc; /* state the inverse fields derive from */
+    if (FWD) {
+        const bool colok = ic0 + cc < g.ncol;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            const int row = rr + 32 * i;
+            cd v = cmk(0.0, 0.0);
+            if (colok) v = a.in[(size_t)(row * g.Y2 + j2) * a.in_pitch + ic0 + cc];
+            S[nsb_sidx(row, cc)] = v;
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int job = FWD ? 0 : 1; job <= (INV ? 4 : 0); ++job) {
+        if (active) {
+            cd x[32];
+            if (job == 0) {
+#pragma unroll
+                for (int m = 0; m < 32; ++m) {
+                    cd v = S[nsb_sidx(lane + 32 * m, warp)];
+                    if (g.Y2 > 1) v = cmul(v, cmul(ta, TB[m]));
+                    x[m] = cmk(v.x, -v.y); /* forward = conj o inverse o conj */
+                }
+                __syncwarp(); /* every lane holds its values before the transpose reuses the slots */
+            } else {
+                const int f = job - 1;
+#pragma unroll
+                for (int m = 0; m < 32; ++m) {
+                    const int j1 = lane + 32 * m;
+                    const int j = j1 * g.Y2 + j2;
+                    cd v = cmk(0.0, 0.0);
+                    if (nsb_iabs(nsb_band(j, g.ny)) <= g.ycut) {
+                        const cd W = Wre[kbase + j1];
+                        const double kyv = __ldg(&kyc[j1]);
+                        cd z = W;
+                        if (f < 2) z = nsb_psi_from_w(W, __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv)));
+                        v = nsb_ik((f & 1) ? kyv : kxv, z);
+                    }
+                    x[m] = v;
+                }
+            }
+            nsb_fft1024_warp_col<true>(x, S, warp, TW, lane);
+            if (job == 0) {
+#pragma unroll
+                for (int m = 0; m < 32; ++m) S[nsb_sidx(lane + 32 * m, warp)] = cmk(x[m].x, -x[m].y);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 32; ++m) {
+                    cd v = x[m];
+                    if (g.Y2 > 1) v = cmulc(v, cmul(ta, TB[m]));
+                    S[nsb_sidx(lane + 32 * m, warp)] = v;
+                }
+            }
+        }
+        __syncthreads();
+        if (job == 0) {
+            /* RK sweep: thread takes elements flat = tid + 128 i of the 4 x 1024 tile */
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i) {
+                const int flat = threadIdx.x + 128 * i;
+                const int c = flat >> 10, j1 = flat & 1023;
+                const int icc = ic0 + c;
+                const int j = j1 * g.Y2 + j2;
+                const int band = nsb_band(j, g.ny);
+                if (icc < g.ncol && nsb_iabs(band) <= g.ycut) {
+                    const cd v = S[nsb_sidx(j1, c)];
+                    const cd Nh = cmk(-(v.x * g.norm), -(v.y * g.norm));
+                    nsb_rk_update(a.rk, ((size_t)icc * g.Y2 + j2) * 1024 + j1, __ldg(&g.kx[icc]), __ldg(&kyc[j1]), icc,
+                                  band, Nh);
+                }
+            }
+        } else {
+            cd *out = a.out + (size_t)(job - 1) * a.out_fs;
+            if (ic0 + cc < g.ncol) {
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) {
+                    const int row = rr + 32 * i;
+                    out[(size_t)(row * g.Y2 + j2) * a.out_pitch + ic0 + cc] = S[nsb_sidx(row, cc)];
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 

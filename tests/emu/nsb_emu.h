@@ -32,6 +32,7 @@
 #define __restrict__ __restrict
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
+#define __shared__ static /* blocks run one at a time on one OS thread */
 
 struct uint3_emu { unsigned x, y, z; };
 struct dim3 {

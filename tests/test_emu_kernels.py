@@ -57,3 +57,17 @@ def test_emu_gamma1024_fast_path(nsb, emu_lib, oracles, nx, ny, plan):
     """X2 == 1024 selects the warp-level register FFT kernel (k_gamma1024)."""
     pc.check_per_step(nsb, emu_lib, oracles, best_oracle_kind(oracles), nx, ny, 2, hv=HV,
                       forcing=dict(kind="white"), **plan)
+
+
+@pytest.mark.parametrize("nx,ny,plan,hv,forcing", [
+    (16, 1024, {}, HV, "white"),
+    (32, 2048, dict(y1=1024), SFD, "colored"),
+])
+def test_emu_alpha1024_fused_path(nsb, emu_lib, oracles, nx, ny, plan, hv, forcing):
+    """Y1 == 1024 selects the fused column kernel (k_alpha1024) and the K-layout state."""
+    pc.check_per_step(nsb, emu_lib, oracles, best_oracle_kind(oracles), nx, ny, 2, hv=hv,
+                      forcing=dict(kind=forcing), **plan)
+
+
+def test_emu_alpha1024_free_running_with_diagnostics(nsb, emu_lib, oracles):
+    pc.check_free_running(nsb, emu_lib, oracles, best_oracle_kind(oracles), 16, 1024, 6, every=3, hv=HV)
