@@ -113,16 +113,17 @@ __device__ __forceinline__ cd nsb_damping(const NsbHv &h, double k2, cd W, const
  * Explicit _rn intrinsics keep nvcc from contracting into FMAs so the pointwise
  * arithmetic rounds like the -ffp-contract=off oracle.
  */
-__device__ __forceinline__ cd nsb_rk_update(const NsbRk &r, size_t idx, double kxv, double kyv, int i,
-                                            int band, cd Nh) {
-    const cd W0v = r.W0[idx];
-    const cd W = (r.stage == 1) ? W0v : r.Wst[idx];
+/* pure arithmetic of one RK mode update: inputs already in registers.
+ * Returns the next state (Wst for stages 1-3, the new omega_hat for stage 4). */
+__device__ __forceinline__ cd nsb_rk_math(const NsbRk &r, double dt, cd W0v, cd Wstv, cd ACCv, cd Sv, double kxv,
+                                          double kyv, int i, int band, cd Nh, cd *acc_out, cd *sfd_out) {
+    const cd W = (r.stage == 1) ? W0v : Wstv;
     const double k2 = __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv));
     cd k;
     k.x = __dsub_rn(Nh.x, __dmul_rn(__dmul_rn(k2, W.x), r.inv_Re));
     k.y = __dsub_rn(Nh.y, __dmul_rn(__dmul_rn(k2, W.y), r.inv_Re));
     if (r.hv.visc || r.hv.sfd) {
-        const cd damp = nsb_damping(r.hv, k2, W, r.SFD, idx);
+        const cd damp = nsb_damping(r.hv, k2, W, &Sv, 0);
         k.x = __dsub_rn(k.x, damp.x);
         k.y = __dsub_rn(k.y, damp.y);
     }
@@ -131,36 +132,46 @@ __device__ __forceinline__ cd nsb_rk_update(const NsbRk &r, size_t idx, double k
         k.x = __dadd_rn(k.x, f.x);
         k.y = __dadd_rn(k.y, f.y);
     }
-    const double dt = *r.dt;
+    *sfd_out = Sv;
     if (r.stage == 1) {
-        r.ACC[idx] = k;
+        *acc_out = k;
         const double c = __dmul_rn(0.5, dt);
-        const cd Wn = cmk(__dadd_rn(W0v.x, __dmul_rn(c, k.x)), __dadd_rn(W0v.y, __dmul_rn(c, k.y)));
-        r.Wst[idx] = Wn;
-        return Wn;
+        return cmk(__dadd_rn(W0v.x, __dmul_rn(c, k.x)), __dadd_rn(W0v.y, __dmul_rn(c, k.y)));
     } else if (r.stage == 2 || r.stage == 3) {
-        const cd a = r.ACC[idx];
-        r.ACC[idx] = cmk(__dadd_rn(a.x, __dmul_rn(2.0, k.x)), __dadd_rn(a.y, __dmul_rn(2.0, k.y)));
+        *acc_out = cmk(__dadd_rn(ACCv.x, __dmul_rn(2.0, k.x)), __dadd_rn(ACCv.y, __dmul_rn(2.0, k.y)));
         const double c = (r.stage == 2) ? __dmul_rn(0.5, dt) : dt;
-        const cd Wn = cmk(__dadd_rn(W0v.x, __dmul_rn(c, k.x)), __dadd_rn(W0v.y, __dmul_rn(c, k.y)));
-        r.Wst[idx] = Wn;
-        return Wn;
-    } else {
-        const cd a = r.ACC[idx];
-        const double c = __ddiv_rn(dt, 6.0);
-        const cd Wn = cmk(__dadd_rn(W0v.x, __dmul_rn(c, __dadd_rn(a.x, k.x))),
-                          __dadd_rn(W0v.y, __dmul_rn(c, __dadd_rn(a.y, k.y))));
-        r.W0[idx] = Wn;
-        if (r.hv.sfd && r.hv.sfd_strength > 0.0 && r.hv.sfd_timescale > 0.0 && dt > 0.0) {
-            double al = __ddiv_rn(dt, r.hv.sfd_timescale);
-            al = al > 1.0 ? 1.0 : (al < 0.0 ? 0.0 : al);
-            const cd S = r.SFD[idx];
-            const double om = __dsub_rn(1.0, al);
-            r.SFD[idx] = cmk(__dadd_rn(__dmul_rn(om, S.x), __dmul_rn(al, Wn.x)),
-                             __dadd_rn(__dmul_rn(om, S.y), __dmul_rn(al, Wn.y)));
-        }
-        return Wn;
+        return cmk(__dadd_rn(W0v.x, __dmul_rn(c, k.x)), __dadd_rn(W0v.y, __dmul_rn(c, k.y)));
     }
+    *acc_out = ACCv;
+    const double c = __ddiv_rn(dt, 6.0);
+    const cd Wn = cmk(__dadd_rn(W0v.x, __dmul_rn(c, __dadd_rn(ACCv.x, k.x))),
+                      __dadd_rn(W0v.y, __dmul_rn(c, __dadd_rn(ACCv.y, k.y))));
+    if (r.hv.sfd && r.hv.sfd_strength > 0.0 && r.hv.sfd_timescale > 0.0 && dt > 0.0) {
+        double al = __ddiv_rn(dt, r.hv.sfd_timescale);
+        al = al > 1.0 ? 1.0 : (al < 0.0 ? 0.0 : al);
+        const double om = __dsub_rn(1.0, al);
+        *sfd_out = cmk(__dadd_rn(__dmul_rn(om, Sv.x), __dmul_rn(al, Wn.x)),
+                       __dadd_rn(__dmul_rn(om, Sv.y), __dmul_rn(al, Wn.y)));
+    }
+    return Wn;
+}
+
+__device__ __forceinline__ cd nsb_rk_update(const NsbRk &r, size_t idx, double kxv, double kyv, int i,
+                                            int band, cd Nh) {
+    const cd W0v = r.W0[idx];
+    const cd Wstv = (r.stage == 1) ? W0v : r.Wst[idx];
+    const cd ACCv = (r.stage == 1) ? cmk(0.0, 0.0) : r.ACC[idx];
+    const cd Sv = (r.hv.sfd) ? r.SFD[idx] : cmk(0.0, 0.0);
+    cd acc, sfd;
+    const cd nxt = nsb_rk_math(r, *r.dt, W0v, Wstv, ACCv, Sv, kxv, kyv, i, band, Nh, &acc, &sfd);
+    if (r.stage < 4) {
+        r.ACC[idx] = acc;
+        r.Wst[idx] = nxt;
+    } else {
+        r.W0[idx] = nxt;
+        if (r.hv.sfd) r.SFD[idx] = sfd;
+    }
+    return nxt;
 }
 
 /* ------------------------------------------------------------------ alpha_inv */
@@ -898,7 +909,7 @@ struct AlphaFastArgs {
 };
 
 #define NSB_A1024_COLS 4
-#define NSB_A1024_SMEM (1024 * 16 + 1024 * NSB_A1024_COLS * 16 + 32 * 16)
+#define NSB_A1024_SMEM (1024 * 16 + 1024 * NSB_A1024_COLS * 16 + 32 * 16 + 1024 * 8)
 
 /* shared tile S[1024 rows][4 columns], 16-byte chunks XOR-swizzled so that row-wise
  * (cooperative, coalesced) and column-wise (per-warp FFT) accesses are both conflict free */
@@ -962,7 +973,8 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
     if (threadIdx.x < 32) TB[threadIdx.x] = __ldg(&g.WY[(size_t)32 * j2 * threadIdx.x]);
     /* y twiddle exp(-2 pi i j2 y1/ny), y1 = lane + 32 m, factored as ta * TB[m] */
     const cd ta = __ldg(&g.WY[(size_t)j2 * lane]);
-    const double *kyc = g.kyK + (size_t)j2 * 1024; /* ky of this CTA's rows, indexed by j1 */
+    double *KY = reinterpret_cast<double *>(TB + 32); /* ky of this CTA's rows, indexed by j1 */
+    for (int k = threadIdx.x; k < 1024; k += blockDim.x) KY[k] = __ldg(&g.kyK[(size_t)j2 * 1024 + k]);
     const double kxv = active ? __ldg(&g.kx[ic]) : 0.0;
     const size_t kbase = ((size_t)ic * g.Y2 + j2) * 1024;
     const cd *Wre = FWD ? a.rk.Wst : a.Wsrc; /* state the inverse fields derive from */
@@ -991,19 +1003,24 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
                 __syncwarp(); /* every lane holds its values before the transpose reuses the slots */
             } else {
                 const int f = job - 1;
+                /* all 32 state loads in flight at once (unconditional: K layout covers every row) */
+#pragma unroll
+                for (int m = 0; m < 32; ++m) x[m] = Wre[kbase + lane + 32 * m];
 #pragma unroll
                 for (int m = 0; m < 32; ++m) {
                     const int j1 = lane + 32 * m;
-                    const int j = j1 * g.Y2 + j2;
-                    cd v = cmk(0.0, 0.0);
-                    if (nsb_iabs(nsb_band(j, g.ny)) <= g.ycut) {
-                        const cd W = Wre[kbase + j1];
-                        const double kyv = __ldg(&kyc[j1]);
-                        cd z = W;
-                        if (f < 2) z = nsb_psi_from_w(W, __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv)));
-                        v = nsb_ik((f & 1) ? kyv : kxv, z);
+                    const bool keep = nsb_iabs(nsb_band(j1 * g.Y2 + j2, g.ny)) <= g.ycut;
+                    const double kyv = KY[j1];
+                    /* i k psi = -i (k/k^2) w for f < 2, i k w otherwise: one reciprocal per mode
+                     * instead of the reference's two divisions (spectral_core.c:17,66); differs
+                     * from it by <= 2 ulp, far inside the 1e-11 parity tolerance */
+                    double kk = (f & 1) ? kyv : kxv;
+                    if (f < 2) {
+                        const double k2 = __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv));
+                        kk = (k2 > 1e-12) ? -(kk * nsb_drcp(k2)) : 0.0;
                     }
-                    x[m] = v;
+                    const cd v = nsb_ik(kk, x[m]);
+                    x[m] = keep ? v : cmk(0.0, 0.0);
                 }
             }
             nsb_fft1024_warp_col<true>(x, S, warp, TW, lane);
@@ -1021,19 +1038,46 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
         }
         __syncthreads();
         if (job == 0) {
-            /* RK sweep: thread takes elements flat = tid + 128 i of the 4 x 1024 tile */
-#pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
-                const int flat = threadIdx.x + 128 * i;
-                const int c = flat >> 10, j1 = flat & 1023;
-                const int icc = ic0 + c;
-                const int j = j1 * g.Y2 + j2;
-                const int band = nsb_band(j, g.ny);
-                if (icc < g.ncol && nsb_iabs(band) <= g.ycut) {
-                    const cd v = S[nsb_sidx(j1, c)];
-                    const cd Nh = cmk(-(v.x * g.norm), -(v.y * g.norm));
-                    nsb_rk_update(a.rk, ((size_t)icc * g.Y2 + j2) * 1024 + j1, __ldg(&g.kx[icc]), __ldg(&kyc[j1]), icc,
-                                  band, Nh);
+            /* RK sweep: thread takes elements flat = tid + 128 i of the 4 x 1024 tile, four at a
+             * time with all state loads issued before the arithmetic */
+            const double dt = *a.rk.dt;
+            const bool use_sfd = a.rk.hv.sfd != 0;
+#pragma unroll 1
+            for (int i0 = 0; i0 < 32; i0 += 4) {
+                cd W0v[4], Wsv[4], ACv[4], SFv[4];
+                size_t kid[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int flat = threadIdx.x + 128 * (i0 + u);
+                    const int c = flat >> 10, j1 = flat & 1023;
+                    int icc = ic0 + c;
+                    if (icc >= g.ncol) icc = g.ncol - 1; /* clamped: loaded, never stored */
+                    kid[u] = ((size_t)icc * g.Y2 + j2) * 1024 + j1;
+                    W0v[u] = a.rk.W0[kid[u]];
+                    Wsv[u] = (a.rk.stage == 1) ? W0v[u] : a.rk.Wst[kid[u]];
+                    ACv[u] = (a.rk.stage == 1) ? cmk(0.0, 0.0) : a.rk.ACC[kid[u]];
+                    SFv[u] = use_sfd ? a.rk.SFD[kid[u]] : cmk(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int flat = threadIdx.x + 128 * (i0 + u);
+                    const int c = flat >> 10, j1 = flat & 1023;
+                    const int icc = ic0 + c;
+                    const int band = nsb_band(j1 * g.Y2 + j2, g.ny);
+                    if (icc < g.ncol && nsb_iabs(band) <= g.ycut) {
+                        const cd v = S[nsb_sidx(j1, c)];
+                        const cd Nh = cmk(-(v.x * g.norm), -(v.y * g.norm));
+                        cd acc, sfd;
+                        const cd nxt = nsb_rk_math(a.rk, dt, W0v[u], Wsv[u], ACv[u], SFv[u], __ldg(&g.kx[icc]), KY[j1],
+                                                   icc, band, Nh, &acc, &sfd);
+                        if (a.rk.stage < 4) {
+                            a.rk.ACC[kid[u]] = acc;
+                            a.rk.Wst[kid[u]] = nxt;
+                        } else {
+                            a.rk.W0[kid[u]] = nxt;
+                            if (use_sfd) a.rk.SFD[kid[u]] = sfd;
+                        }
+                    }
                 }
             }
         } else {

@@ -22,6 +22,13 @@
 
 typedef double2 cd; /* complex double: x = re, y = im */
 
+/* correctly rounded FP64 reciprocal (MUFU.RCP64H + Newton, inlined: no division subroutine) */
+#ifdef NSB_EMULATE
+static inline double nsb_drcp(double a) { return 1.0 / a; }
+#else
+__device__ __forceinline__ double nsb_drcp(double a) { return __drcp_rn(a); }
+#endif
+
 /*
  * TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers. global -> shared,
  * completion counted in bytes on an mbarrier in shared memory. Addresses and sizes must be
