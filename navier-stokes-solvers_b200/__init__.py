@@ -197,6 +197,9 @@ class NsbContext:
         b = (C.c_int * n)(*dsts)
         self._ck(self.lib.nsb_spectral_to_physical(self.h, n, a, b))
 
+    def apply_dealiasing(self, field):
+        self._ck(self.lib.nsb_apply_dealiasing(self.h, field))
+
     def velocity_from_vorticity(self):
         self._ck(self.lib.nsb_velocity_from_vorticity(self.h))
 

@@ -1,0 +1,635 @@
+/*
+ * nsb_chain.cuh -- the physical-space "chain" of one RK stage for X2 == 1024:
+ *
+ *      T --B--> Z --G--> P --F--> T'
+ *
+ *   B  (was k_beta_inv)   length-Y2 DFT over j2, Hermitian gather, length-X1 DFT over k1,
+ *                         x twiddle, and the Hermitian PACKING of two real fields into one
+ *                         complex comb spectrum: Z1 = psi_x + i omega_y, Z2 = psi_y + i omega_x
+ *   G  (was k_gamma1024)  per comb: inverse warp FFT-1024 of Z1 and Z2; because of the
+ *                         packing the Jacobian is Re*Im of one transform minus Re*Im of the
+ *                         other (spectral_core.c:103), so only one real product (8 KB) is
+ *                         parked per comb; forward warp FFT-1024 of J(comb 0) + i J(comb 1)
+ *   F  (was k_beta_fwd)   split of the packed forward spectrum, x twiddle, length-X1 DFT,
+ *                         length-Y2 DFT -> T'
+ *
+ * The work unit is a SLAB of 16 y rows (GY = 16/Y2 consecutive y1 values): B produces the
+ * 16*X1 combs of a slab at once, G consumes them pair by pair, F needs all of them.
+ *
+ * Two ways to run it:
+ *   - three plain kernels (k_chain_B / k_chain_G / k_chain_F), Z and P full size in HBM;
+ *   - ONE persistent kernel (k_chain): CTAs draw items from an ordered ticket queue
+ *     [F(s-lG-lF) G(s-lG) B(s)] for s = 0.., wait on per-slab completion counters
+ *     (release/acquire in global memory) and keep Z and P in small RINGS that stay
+ *     resident in the 126 MB L2, so the 4+4+1+1 array passes between B, G and F never
+ *     reach HBM. Every item only waits on items with smaller tickets, all CTAs are
+ *     co-resident (grid <= SMs x occupancy), hence no deadlock.
+ *
+ * Replaces, for the hot path: spectral_transforms.c:25-32 (c2r), spectral_core.c:101-111
+ * (Jacobian + r2c) and spectral_time_integration.c:14-20 (max |u|).
+ */
+#ifndef NSB_CHAIN_CUH
+#define NSB_CHAIN_CUH
+
+#include "nsb_kernels.cuh"
+
+#define NSB_CH_ROWS 16
+
+struct ChainArgs {
+    const cd *T; /* alpha output, 4 fields (stride fsT, pitch PT) */
+    cd *Tp;      /* F output = alpha_fwd input (pitch PT) */
+    cd *Z;       /* [slot][pp][q][1024] packed comb spectra */
+    cd *P;       /* [slot][pair][1024] packed forward spectra */
+    int nslab;   /* ny / 16 */
+    int nslotZ, nslotP;
+    int GY;      /* y1 values per slab = 16 / Y2 */
+    int NQ;      /* combs per slab = 16 * X1 */
+    int nbatch;  /* k2 batches */
+    int nd, nm;  /* direct / mirror column segments (nsb_beta_segs) */
+    unsigned long long *umax_bits;
+    /* persistent mode */
+    unsigned *ctr; /* [0] ticket, [1 + s] doneB, [1 + nslab + s] doneG, [1 + 2 nslab + s] doneF */
+    int leadG, leadF;
+};
+
+/* ------------------------------------------------------------------ B items */
+
+template <int Y2>
+__device__ __forceinline__ void chain_B_step1(const NsbGeom &g, const ChainArgs &a, cd *tile, int slab, int pp,
+                                              int kb) {
+    const int nseg = a.nd + a.nm;
+    const int fa = pp == 0 ? 0 : 1, fb = pp == 0 ? 3 : 2;
+    const int per_g = nseg * g.BC, per_f = a.GY * per_g;
+    for (int w = threadIdx.x; w < 2 * per_f; w += blockDim.x) {
+        const int fi = w / per_f;
+        int r = w - fi * per_f;
+        const int gy = r / per_g;
+        r -= gy * per_g;
+        const int seg = r / g.BC, cc = r - seg * g.BC;
+        const int col = nsb_beta_col(g, seg, a.nd, kb, cc, false);
+        const int y1 = slab * a.GY + gy;
+        cd x[Y2];
+        if (col >= 0) {
+            const cd *in = a.T + (size_t)(fi ? fb : fa) * g.fsT + (size_t)(y1 * Y2) * g.PT + col;
+#pragma unroll
+            for (int j2 = 0; j2 < Y2; ++j2) x[j2] = nsb_ldcs(&in[(size_t)j2 * g.PT]);
+            nsb_dft<Y2, true>(x);
+        } else {
+#pragma unroll
+            for (int j2 = 0; j2 < Y2; ++j2) x[j2] = cmk(0.0, 0.0);
+        }
+#pragma unroll
+        for (int y2 = 0; y2 < Y2; ++y2)
+            tile[(size_t)((fi * NSB_CH_ROWS + gy * Y2 + y2) * nseg + seg) * g.BC + cc] = x[y2];
+    }
+}
+
+template <int X1>
+__device__ __forceinline__ void chain_gather(cd (&x)[X1], const cd *tile, int row, int nseg, int nd, int nm, int BC,
+                                             int cc) {
+#pragma unroll
+    for (int k1 = 0; k1 < X1; ++k1) {
+        if (X1 == 1 || k1 < X1 / 2) {
+            x[k1] = (k1 < nd) ? tile[(size_t)(row * nseg + k1) * BC + cc] : cmk(0.0, 0.0);
+        } else {
+            const int kp = X1 - 1 - k1;
+            x[k1] = (kp < nm) ? cconj(tile[(size_t)(row * nseg + nd + kp) * BC + cc]) : cmk(0.0, 0.0);
+        }
+    }
+}
+
+template <int X1>
+__device__ __forceinline__ void chain_B_step2(const NsbGeom &g, const ChainArgs &a, const cd *tile, int slot, int pp,
+                                              int kb) {
+    const int nseg = a.nd + a.nm;
+    for (int w = threadIdx.x; w < NSB_CH_ROWS * g.BC; w += blockDim.x) {
+        const int r = w / g.BC, cc = w - r * g.BC;
+        const int k2 = kb + cc;
+        if (k2 > g.X2h) continue;
+        cd A[X1], B[X1];
+        chain_gather<X1>(A, tile, r, nseg, a.nd, a.nm, g.BC, cc);
+        chain_gather<X1>(B, tile, NSB_CH_ROWS + r, nseg, a.nd, a.nm, g.BC, cc);
+        if (k2 == 0) { /* FFTW c2r ignores Im of the kx = 0 bin */
+            A[0].y = 0.0;
+            B[0].y = 0.0;
+        }
+        nsb_dft<X1, true>(A);
+        nsb_dft<X1, true>(B);
+        cd *zo = a.Z + ((size_t)(slot * 2 + pp) * a.NQ + (size_t)r * X1) * 1024;
+#pragma unroll
+        for (int x1 = 0; x1 < X1; ++x1) {
+            cd av = A[x1], bv = B[x1];
+            if (X1 > 1) {
+                const cd tw = __ldg(&g.WX[(size_t)k2 * x1]);
+                av = cmulc(av, tw);
+                bv = cmulc(bv, tw);
+            }
+            cd *row = zo + (size_t)x1 * 1024;
+            /* Z[k] = A[k] + i B[k]; Z[1024-k] = conj(A[k]) + i conj(B[k]) */
+            if (k2 == 0 || k2 == g.X2h) {
+                row[k2] = cmk(av.x, bv.x);
+            } else {
+                row[k2] = cmk(av.x - bv.y, av.y + bv.x);
+                row[1024 - k2] = cmk(av.x + bv.y, bv.x - av.y);
+            }
+        }
+    }
+}
+
+/* item = (slab, pp, batch); tile: 2 * 16 * nseg * BC complex. All threads call. */
+__device__ __forceinline__ void chain_B_item(const NsbGeom &g, const ChainArgs &a, cd *tile, int slab, int slot,
+                                             int pp, int batch) {
+    const int kb = batch * g.BC;
+    switch (g.Y2) {
+        case 1: chain_B_step1<1>(g, a, tile, slab, pp, kb); break;
+        case 2: chain_B_step1<2>(g, a, tile, slab, pp, kb); break;
+        case 4: chain_B_step1<4>(g, a, tile, slab, pp, kb); break;
+        case 8: chain_B_step1<8>(g, a, tile, slab, pp, kb); break;
+        default: chain_B_step1<16>(g, a, tile, slab, pp, kb); break;
+    }
+    __syncthreads();
+    switch (g.X1) {
+        case 1: chain_B_step2<1>(g, a, tile, slot, pp, kb); break;
+        case 2: chain_B_step2<2>(g, a, tile, slot, pp, kb); break;
+        case 4: chain_B_step2<4>(g, a, tile, slot, pp, kb); break;
+        case 8: chain_B_step2<8>(g, a, tile, slot, pp, kb); break;
+        default: chain_B_step2<16>(g, a, tile, slot, pp, kb); break;
+    }
+}
+
+/* ------------------------------------------------------------------ G items */
+
+/* per-warp shared memory of a G item: transpose buffer (32x32 doubles, XOR swizzled) |
+ * parked products / J of the two combs (2 x 1024 doubles) | psi_x of the current comb (UMAX) */
+#define NSB_CHG_WARP_BYTES(UMAX) (8192 + 16384 + ((UMAX) ? 8192 : 0))
+#define NSB_CH_TW_BYTES (1024 * 16)
+
+/* warp FFT-1024 (nsb_fft1024.cuh) with an unpadded, XOR-swizzled 8 KB transpose buffer */
+template <bool INV>
+__device__ __forceinline__ void nsb_fft1024_warp_sw(cd (&x)[32], double *T, const cd *TW, int lane) {
+    nsb_dft32<INV>(x);
+#pragma unroll
+    for (int r = 1; r < 32; ++r) {
+        const cd tw = TW[r * 32 + lane];
+        x[r] = INV ? cmulc(x[r], tw) : cmul(x[r], tw);
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r) T[r * 32 + (lane ^ r)] = x[r].x;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 32; ++q) x[q].x = T[lane * 32 + (q ^ lane)];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; ++r) T[r * 32 + (lane ^ r)] = x[r].y;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 32; ++q) x[q].y = T[lane * 32 + (q ^ lane)];
+    __syncwarp();
+    nsb_dft32<INV>(x);
+}
+
+/* one comb pair by one warp. wb: this warp's NSB_CHG_WARP_BYTES; returns max |u|^2 seen */
+template <bool UMAX>
+__device__ __forceinline__ double chain_G_pair(const cd *z1base, const cd *z2base, cd *pout, unsigned char *wb,
+                                               const cd *TW, int lane) {
+    double *T = reinterpret_cast<double *>(wb);
+    double *PK = reinterpret_cast<double *>(wb + 8192);
+    double *PX = reinterpret_cast<double *>(wb + 8192 + 16384);
+    double umax = 0.0;
+    cd x[32];
+#pragma unroll 1
+    for (int comb = 0; comb < 2; ++comb) {
+        const cd *z1 = z1base + (size_t)comb * 1024, *z2 = z2base + (size_t)comb * 1024;
+#pragma unroll
+        for (int m = 0; m < 32; ++m) x[m] = nsb_ldcg(&z1[lane + 32 * m]);
+        /* pull the next 16 KB input towards L2 while this transform runs */
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nsb_prefetch_l2(reinterpret_cast<const char *>(z2) + (lane * 4 + i) * 128);
+        nsb_fft1024_warp_sw<true>(x, T, TW, lane); /* x = psi_x + i omega_y */
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {
+            PK[comb * 1024 + m * 32 + lane] = __dmul_rn(x[m].x, x[m].y);
+            if (UMAX) PX[m * 32 + lane] = x[m].x;
+        }
+#pragma unroll
+        for (int m = 0; m < 32; ++m) x[m] = nsb_ldcg(&z2[lane + 32 * m]);
+        if (comb == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                nsb_prefetch_l2(reinterpret_cast<const char *>(z1base + 1024) + (lane * 4 + i) * 128);
+        }
+        nsb_fft1024_warp_sw<true>(x, T, TW, lane); /* x = psi_y + i omega_x */
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {
+            /* spectral_core.c:103 : J = psi_x*omega_y - psi_y*omega_x */
+            const double J = __dsub_rn(PK[comb * 1024 + m * 32 + lane], __dmul_rn(x[m].x, x[m].y));
+            if (UMAX) { /* spectral_time_integration.c:16 : |u|^2 = psi_y^2 + psi_x^2 */
+                const double px = PX[m * 32 + lane];
+                umax = fmax(umax, __dadd_rn(__dmul_rn(x[m].x, x[m].x), __dmul_rn(px, px)));
+            }
+            if (comb == 0) PK[m * 32 + lane] = J;
+            else x[m] = cmk(PK[m * 32 + lane], J);
+        }
+    }
+    nsb_fft1024_warp_sw<false>(x, T, TW, lane);
+#pragma unroll
+    for (int m = 0; m < 32; ++m) pout[lane + 32 * m] = x[m];
+    return umax;
+}
+
+/* item = (slab, group of W pairs). ub: W * NSB_CHG_WARP_BYTES. */
+template <bool UMAX>
+__device__ __forceinline__ void chain_G_item(const ChainArgs &a, unsigned char *ub, const cd *TW, int slotZ, int slotP,
+                                             int group) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int NP = a.NQ >> 1;
+    const int pair = group * W + warp;
+    if (pair >= NP) return;
+    const cd *z1 = a.Z + ((size_t)(slotZ * 2 + 0) * a.NQ + 2 * pair) * 1024;
+    const cd *z2 = a.Z + ((size_t)(slotZ * 2 + 1) * a.NQ + 2 * pair) * 1024;
+    cd *po = a.P + ((size_t)slotP * NP + pair) * 1024;
+    double umax = chain_G_pair<UMAX>(z1, z2, po, ub + (size_t)warp * NSB_CHG_WARP_BYTES(UMAX), TW, lane);
+    if (UMAX) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, off));
+        if (lane == 0) atomicMax(a.umax_bits, (unsigned long long)__double_as_longlong(umax));
+    }
+}
+
+/* ------------------------------------------------------------------ F items */
+
+template <int X1>
+__device__ __forceinline__ void chain_F_step1(const NsbGeom &g, const ChainArgs &a, cd *tile, int slot, int kb) {
+    const int nseg = a.nd + a.nm;
+    const int NP = a.NQ >> 1;
+    for (int w = threadIdx.x; w < NSB_CH_ROWS * g.BC; w += blockDim.x) {
+        const int r = w / g.BC, cc = w - r * g.BC;
+        const int k2 = kb + cc;
+        cd x[X1];
+        if (k2 <= g.X2h) {
+            const int km = (1024 - k2) & 1023;
+            if (X1 == 1) {
+                const cd *pr = a.P + ((size_t)slot * NP + (r >> 1)) * 1024;
+                const cd Pk = nsb_ldcg(&pr[k2]), Q = nsb_ldcg(&pr[km]);
+                x[0] = (r & 1) ? cmk(0.5 * (Pk.y + Q.y), -0.5 * (Pk.x - Q.x)) : cmk(0.5 * (Pk.x + Q.x), 0.5 * (Pk.y - Q.y));
+            } else {
+#pragma unroll
+                for (int i = 0; i < X1 / 2; ++i) {
+                    const cd *pr = a.P + ((size_t)slot * NP + (size_t)(r * X1) / 2 + i) * 1024;
+                    const cd Pk = nsb_ldcg(&pr[k2]), Q = nsb_ldcg(&pr[km]);
+                    const cd e = cmk(0.5 * (Pk.x + Q.x), 0.5 * (Pk.y - Q.y));
+                    const cd o = cmk(0.5 * (Pk.y + Q.y), -0.5 * (Pk.x - Q.x));
+                    x[2 * i] = cmul(e, __ldg(&g.WX[(size_t)k2 * (2 * i)]));
+                    x[2 * i + 1] = cmul(o, __ldg(&g.WX[(size_t)k2 * (2 * i + 1)]));
+                }
+            }
+            nsb_dft<X1, false>(x);
+        } else {
+#pragma unroll
+            for (int x1 = 0; x1 < X1; ++x1) x[x1] = cmk(0.0, 0.0);
+        }
+#pragma unroll
+        for (int m = 0; m < X1; ++m) {
+            if (X1 == 1 || m < X1 / 2) {
+                if (m < a.nd) tile[(size_t)(r * nseg + m) * g.BC + cc] = x[m];
+            } else {
+                const int kp = X1 - 1 - m;
+                if (kp < a.nm) tile[(size_t)(r * nseg + a.nd + kp) * g.BC + cc] = cconj(x[m]);
+            }
+        }
+    }
+}
+
+template <int Y2>
+__device__ __forceinline__ void chain_F_step2(const NsbGeom &g, const ChainArgs &a, const cd *tile, int slab, int kb) {
+    const int nseg = a.nd + a.nm;
+    const int per_g = nseg * g.BC;
+    for (int w = threadIdx.x; w < a.GY * per_g; w += blockDim.x) {
+        const int gy = w / per_g;
+        const int r = w - gy * per_g;
+        const int seg = r / g.BC, cc = r - seg * g.BC;
+        const int col = nsb_beta_col(g, seg, a.nd, kb, cc, true);
+        if (col < 0) continue;
+        cd x[Y2];
+#pragma unroll
+        for (int y2 = 0; y2 < Y2; ++y2) x[y2] = tile[(size_t)((gy * Y2 + y2) * nseg + seg) * g.BC + cc];
+        nsb_dft<Y2, false>(x);
+        cd *out = a.Tp + (size_t)((slab * a.GY + gy) * Y2) * g.PT + col;
+#pragma unroll
+        for (int j2 = 0; j2 < Y2; ++j2) nsb_stcs(&out[(size_t)j2 * g.PT], x[j2]);
+    }
+}
+
+/* item = (slab, batch); tile: 16 * nseg * BC complex. All threads call. */
+__device__ __forceinline__ void chain_F_item(const NsbGeom &g, const ChainArgs &a, cd *tile, int slab, int slot,
+                                             int batch) {
+    const int kb = batch * g.BC;
+    switch (g.X1) {
+        case 1: chain_F_step1<1>(g, a, tile, slot, kb); break;
+        case 2: chain_F_step1<2>(g, a, tile, slot, kb); break;
+        case 4: chain_F_step1<4>(g, a, tile, slot, kb); break;
+        case 8: chain_F_step1<8>(g, a, tile, slot, kb); break;
+        default: chain_F_step1<16>(g, a, tile, slot, kb); break;
+    }
+    __syncthreads();
+    switch (g.Y2) {
+        case 1: chain_F_step2<1>(g, a, tile, slab, kb); break;
+        case 2: chain_F_step2<2>(g, a, tile, slab, kb); break;
+        case 4: chain_F_step2<4>(g, a, tile, slab, kb); break;
+        case 8: chain_F_step2<8>(g, a, tile, slab, kb); break;
+        default: chain_F_step2<16>(g, a, tile, slab, kb); break;
+    }
+}
+
+/* ------------------------------------------------ B, TMA-fed and persistent */
+
+/*
+ * Valid part of column segment `seg` for the k2 batch starting at kb, in ASCENDING memory
+ * order: `cnt` complex values starting at column `col0`, landing at tile positions
+ * pos0 .. pos0+cnt-1. Direct segments hold k2 = kb + pos, mirror segments hold
+ * k2 = kb + (BC-1-pos) (their columns run backwards in k2).
+ */
+__device__ __forceinline__ void chain_seg_range(const NsbGeom &g, int nd, int seg, int kb, int *pos0, int *cnt,
+                                                int *col0) {
+    if (seg < nd) {
+        int n = g.BC;
+        if (g.X2h + 1 - kb < n) n = g.X2h + 1 - kb;
+        if (g.imax + 1 - seg * g.X2 - kb < n) n = g.imax + 1 - seg * g.X2 - kb;
+        *pos0 = 0;
+        *cnt = n > 0 ? n : 0;
+        *col0 = seg * g.X2 + kb;
+    } else {
+        const int base = (seg - nd) * g.X2 + g.X2 - kb; /* column of cc = 0 */
+        int cmin = base - g.imax;
+        if (cmin < 0) cmin = 0;
+        int cmax = g.BC - 1;
+        if (g.X2h - kb < cmax) cmax = g.X2h - kb;
+        *pos0 = g.BC - 1 - cmax;
+        *cnt = cmax >= cmin ? cmax - cmin + 1 : 0;
+        *col0 = base - cmax;
+    }
+}
+
+/* TMA bulk copies (cp.async.bulk, one 16*cnt-byte row segment per copy, issued by all threads)
+ * of the raw input of item (slab, pp, batch) into `tile`; completion on `bar`. */
+__device__ __forceinline__ void chain_B_issue(const NsbGeom &g, const ChainArgs &a, cd *tile, nsb_mbar_t *bar, int slab,
+                                              int pp, int kb) {
+    const int nseg = a.nd + a.nm;
+    const int rows = 2 * NSB_CH_ROWS; /* (field, gy, j2) */
+    if (threadIdx.x == 0) {
+        unsigned total = 0;
+        for (int seg = 0; seg < nseg; ++seg) {
+            int p0, cnt, c0;
+            chain_seg_range(g, a.nd, seg, kb, &p0, &cnt, &c0);
+            total += (unsigned)cnt * 16u * (unsigned)rows;
+        }
+        nsb_fence_proxy_async();
+        nsb_mbar_expect_tx(bar, total);
+    }
+    __syncthreads();
+    const int fa = pp == 0 ? 0 : 1, fb = pp == 0 ? 3 : 2;
+    for (int w = threadIdx.x; w < rows * nseg; w += blockDim.x) {
+        const int row = w / nseg, seg = w - row * nseg; /* row = fi*16 + gy*Y2 + j2 */
+        int p0, cnt, c0;
+        chain_seg_range(g, a.nd, seg, kb, &p0, &cnt, &c0);
+        if (cnt <= 0) continue;
+        const int fi = row / NSB_CH_ROWS, rr = row - fi * NSB_CH_ROWS;
+        const cd *src = a.T + (size_t)(fi ? fb : fa) * g.fsT + (size_t)(slab * NSB_CH_ROWS + rr) * g.PT + c0;
+        nsb_bulk_g2s(tile + (size_t)(row * nseg + seg) * g.BC + p0, src, (unsigned)cnt * 16u, bar);
+    }
+}
+
+/* step 1 on a TMA-landed tile, in place: positions outside the valid range become zeros */
+template <int Y2>
+__device__ __forceinline__ void chain_B2_step1(const NsbGeom &g, const ChainArgs &a, cd *tile, int kb) {
+    const int nseg = a.nd + a.nm;
+    const int per_g = nseg * g.BC, per_f = a.GY * per_g;
+    for (int w = threadIdx.x; w < 2 * per_f; w += blockDim.x) {
+        const int fi = w / per_f;
+        int r = w - fi * per_f;
+        const int gy = r / per_g;
+        r -= gy * per_g;
+        const int seg = r / g.BC, pos = r - seg * g.BC;
+        int p0, cnt, c0;
+        chain_seg_range(g, a.nd, seg, kb, &p0, &cnt, &c0);
+        cd *col = tile + (size_t)((fi * NSB_CH_ROWS + gy * Y2) * nseg + seg) * g.BC + pos;
+        const size_t rs = (size_t)nseg * g.BC;
+        cd x[Y2];
+        if (pos >= p0 && pos < p0 + cnt) {
+#pragma unroll
+            for (int j2 = 0; j2 < Y2; ++j2) x[j2] = col[j2 * rs];
+            nsb_dft<Y2, true>(x);
+        } else {
+#pragma unroll
+            for (int j2 = 0; j2 < Y2; ++j2) x[j2] = cmk(0.0, 0.0);
+        }
+#pragma unroll
+        for (int y2 = 0; y2 < Y2; ++y2) col[y2 * rs] = x[y2];
+    }
+}
+
+/* gather for tiles in memory order (mirror segments reversed) */
+template <int X1>
+__device__ __forceinline__ void chain_gather_mo(cd (&x)[X1], const cd *tile, int row, int nseg, int nd, int nm, int BC,
+                                                int cc) {
+#pragma unroll
+    for (int k1 = 0; k1 < X1; ++k1) {
+        if (X1 == 1 || k1 < X1 / 2) {
+            x[k1] = (k1 < nd) ? tile[(size_t)(row * nseg + k1) * BC + cc] : cmk(0.0, 0.0);
+        } else {
+            const int kp = X1 - 1 - k1;
+            x[k1] = (kp < nm) ? cconj(tile[(size_t)(row * nseg + nd + kp) * BC + (BC - 1 - cc)]) : cmk(0.0, 0.0);
+        }
+    }
+}
+
+template <int X1, bool MO>
+__device__ __forceinline__ void chain_B_step2x(const NsbGeom &g, const ChainArgs &a, const cd *tile, int slot, int pp,
+                                               int kb) {
+    const int nseg = a.nd + a.nm;
+    for (int w = threadIdx.x; w < NSB_CH_ROWS * g.BC; w += blockDim.x) {
+        const int r = w / g.BC, cc = w - r * g.BC;
+        const int k2 = kb + cc;
+        if (k2 > g.X2h) continue;
+        cd A[X1], B[X1];
+        if (MO) {
+            chain_gather_mo<X1>(A, tile, r, nseg, a.nd, a.nm, g.BC, cc);
+            chain_gather_mo<X1>(B, tile, NSB_CH_ROWS + r, nseg, a.nd, a.nm, g.BC, cc);
+        } else {
+            chain_gather<X1>(A, tile, r, nseg, a.nd, a.nm, g.BC, cc);
+            chain_gather<X1>(B, tile, NSB_CH_ROWS + r, nseg, a.nd, a.nm, g.BC, cc);
+        }
+        if (k2 == 0) { /* FFTW c2r ignores Im of the kx = 0 bin */
+            A[0].y = 0.0;
+            B[0].y = 0.0;
+        }
+        nsb_dft<X1, true>(A);
+        nsb_dft<X1, true>(B);
+        cd *zo = a.Z + ((size_t)(slot * 2 + pp) * a.NQ + (size_t)r * X1) * 1024;
+#pragma unroll
+        for (int x1 = 0; x1 < X1; ++x1) {
+            cd av = A[x1], bv = B[x1];
+            if (X1 > 1) {
+                const cd tw = __ldg(&g.WX[(size_t)k2 * x1]);
+                av = cmulc(av, tw);
+                bv = cmulc(bv, tw);
+            }
+            cd *row = zo + (size_t)x1 * 1024;
+            /* Z[k] = A[k] + i B[k]; Z[1024-k] = conj(A[k]) + i conj(B[k]) */
+            if (k2 == 0 || k2 == g.X2h) {
+                row[k2] = cmk(av.x, bv.x);
+            } else {
+                row[k2] = cmk(av.x - bv.y, av.y + bv.x);
+                row[1024 - k2] = cmk(av.x + bv.y, bv.x - av.y);
+            }
+        }
+    }
+}
+
+/*
+ * Persistent, TMA-fed B: grid = SMs, each CTA walks items blockIdx.x + n*gridDim.x
+ * (item = (slab, pp, batch), batch fastest). Two shared-memory stages: while the CTA
+ * transforms the tile of item n, the bulk copies of item n+1 are in flight, so HBM latency
+ * is off the critical path with one CTA per SM.
+ * smem: 2 stages x (2*16*nseg*BC complex) + 2 mbarriers.
+ */
+__global__ void __launch_bounds__(256, 1) k_chain_B_tma(NsbGeom g, ChainArgs a) {
+    NSB_DYN_SMEM(cd, smem);
+    const int nseg = a.nd + a.nm;
+    const size_t tile_elems = (size_t)2 * NSB_CH_ROWS * nseg * g.BC;
+    nsb_mbar_t *bars = reinterpret_cast<nsb_mbar_t *>(smem + 2 * tile_elems);
+    if (threadIdx.x == 0) {
+        nsb_mbar_init(&bars[0], 1);
+        nsb_mbar_init(&bars[1], 1);
+    }
+    __syncthreads();
+    const int nitems = a.nslab * 2 * a.nbatch;
+    unsigned phase[2] = {0u, 0u};
+    int item = blockIdx.x;
+    if (item < nitems) {
+        const int slab = item / (2 * a.nbatch), rem = item - slab * 2 * a.nbatch;
+        chain_B_issue(g, a, smem, &bars[0], slab, rem / a.nbatch, (rem % a.nbatch) * g.BC);
+    }
+    for (int n = 0; item < nitems; ++n, item += gridDim.x) {
+        const int st = n & 1;
+        const int next = item + gridDim.x;
+        if (next < nitems) {
+            const int slab = next / (2 * a.nbatch), rem = next - slab * 2 * a.nbatch;
+            chain_B_issue(g, a, smem + (size_t)(st ^ 1) * tile_elems, &bars[st ^ 1], slab, rem / a.nbatch,
+                          (rem % a.nbatch) * g.BC);
+        }
+        nsb_mbar_wait(&bars[st], phase[st]);
+        phase[st] ^= 1u;
+        cd *tile = smem + (size_t)st * tile_elems;
+        const int slab = item / (2 * a.nbatch), rem = item - slab * 2 * a.nbatch;
+        const int pp = rem / a.nbatch, kb = (rem % a.nbatch) * g.BC;
+        switch (g.Y2) {
+            case 1: chain_B2_step1<1>(g, a, tile, kb); break;
+            case 2: chain_B2_step1<2>(g, a, tile, kb); break;
+            case 4: chain_B2_step1<4>(g, a, tile, kb); break;
+            case 8: chain_B2_step1<8>(g, a, tile, kb); break;
+            default: chain_B2_step1<16>(g, a, tile, kb); break;
+        }
+        __syncthreads();
+        const int slot = slab % a.nslotZ;
+        switch (g.X1) {
+            case 1: chain_B_step2x<1, true>(g, a, tile, slot, pp, kb); break;
+            case 2: chain_B_step2x<2, true>(g, a, tile, slot, pp, kb); break;
+            case 4: chain_B_step2x<4, true>(g, a, tile, slot, pp, kb); break;
+            case 8: chain_B_step2x<8, true>(g, a, tile, slot, pp, kb); break;
+            default: chain_B_step2x<16, true>(g, a, tile, slot, pp, kb); break;
+        }
+        __syncthreads(); /* the tile is free for the copies of item n+2 */
+    }
+}
+
+/* ------------------------------------------------ the three plain kernels */
+
+/* grid (nbatch, 2, nslab) */
+__global__ void __launch_bounds__(256, 2) k_chain_B(NsbGeom g, ChainArgs a) {
+    NSB_DYN_SMEM(cd, tile);
+    chain_B_item(g, a, tile, blockIdx.z, blockIdx.z % a.nslotZ, blockIdx.y, blockIdx.x);
+}
+
+/* grid (groups per slab, nslab), W warps */
+template <bool UMAX>
+__global__ void __launch_bounds__(256, 1) k_chain_G(NsbGeom g, ChainArgs a) {
+    NSB_DYN_SMEM(unsigned char, raw);
+    cd *TW = reinterpret_cast<cd *>(raw);
+    nsb_fill_tw1024(TW, g.WX, g.nx / 1024);
+    __syncthreads();
+    chain_G_item<UMAX>(a, raw + NSB_CH_TW_BYTES, TW, blockIdx.y % a.nslotZ, blockIdx.y % a.nslotP, blockIdx.x);
+}
+
+/* grid (nbatch, nslab) */
+__global__ void __launch_bounds__(256) k_chain_F(NsbGeom g, ChainArgs a) {
+    NSB_DYN_SMEM(cd, tile);
+    chain_F_item(g, a, tile, blockIdx.y, blockIdx.y % a.nslotP, blockIdx.x);
+}
+
+/* ------------------------------------------------ the persistent dataflow kernel */
+
+__device__ __forceinline__ void chain_wait(const unsigned *ctr, unsigned need) {
+    if (threadIdx.x == 0) {
+        while (nsb_ld_acquire(ctr) < need) nsb_backoff();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void chain_signal(unsigned *ctr) {
+    __syncthreads();
+    if (threadIdx.x == 0) nsb_red_release(ctr, 1u);
+}
+
+template <bool UMAX, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_chain(NsbGeom g, ChainArgs a) {
+    NSB_DYN_SMEM(unsigned char, raw);
+    __shared__ unsigned s_ticket[2];
+    cd *TW = reinterpret_cast<cd *>(raw);
+    unsigned char *ub = raw + NSB_CH_TW_BYTES;
+    cd *tile = reinterpret_cast<cd *>(ub);
+    nsb_fill_tw1024(TW, g.WX, g.nx / 1024);
+    const int W = blockDim.x >> 5;
+    const int NP = a.NQ >> 1;
+    const int nB = 2 * a.nbatch, nG = (NP + W - 1) / W, nF = a.nbatch;
+    const int per = nF + nG + nB;
+    const unsigned total = (unsigned)(a.nslab + a.leadG + a.leadF) * (unsigned)per;
+    unsigned *doneB = a.ctr + 1, *doneG = a.ctr + 1 + a.nslab, *doneF = a.ctr + 1 + 2 * a.nslab;
+    if (threadIdx.x == 0) s_ticket[0] = atomicAdd(a.ctr, 1u);
+    __syncthreads();
+    for (int it = 0;; ++it) {
+        const unsigned ticket = s_ticket[it & 1];
+        if (ticket >= total) break;
+        /* the next ticket is drawn now so that its latency hides behind this item */
+        if (threadIdx.x == 0) s_ticket[(it + 1) & 1] = atomicAdd(a.ctr, 1u);
+        const int step = (int)(ticket / (unsigned)per);
+        int idx = (int)(ticket - (unsigned)step * (unsigned)per);
+        if (idx < nF) { /* F of slab step - leadG - leadF */
+            const int s = step - a.leadG - a.leadF;
+            if (s >= 0 && s < a.nslab) {
+                chain_wait(&doneG[s], (unsigned)nG);
+                chain_F_item(g, a, tile, s, s % a.nslotP, idx);
+                chain_signal(&doneF[s]);
+            }
+        } else if (idx < nF + nG) { /* G of slab step - leadG */
+            const int s = step - a.leadG;
+            if (s >= 0 && s < a.nslab) {
+                chain_wait(&doneB[s], (unsigned)nB);
+                if (s >= a.nslotP) chain_wait(&doneF[s - a.nslotP], (unsigned)nF);
+                chain_G_item<UMAX>(a, ub, TW, s % a.nslotZ, s % a.nslotP, idx - nF);
+                chain_signal(&doneG[s]);
+            }
+        } else { /* B of slab step */
+            const int s = step;
+            if (s < a.nslab) {
+                if (s >= a.nslotZ) chain_wait(&doneG[s - a.nslotZ], (unsigned)nG);
+                idx -= nF + nG;
+                chain_B_item(g, a, tile, s, s % a.nslotZ, idx / a.nbatch, idx % a.nbatch);
+                chain_signal(&doneB[s]);
+            }
+        }
+        __syncthreads(); /* tile / per-warp buffers are reused by the next item; s_ticket visible */
+    }
+}
+
+#endif

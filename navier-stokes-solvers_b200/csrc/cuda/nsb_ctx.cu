@@ -4,6 +4,7 @@
  * nsb_kernels.cuh / nsb_fft.cuh.
  */
 #include "nsb_kernels.cuh"
+#include "nsb_chain.cuh"
 #include "../../../include/nsb.h"
 
 #include <cmath>
@@ -70,6 +71,12 @@ struct nsb_ctx {
     /* K-layout copies of the RK state used by the fused column kernel (k_alpha1024) */
     cd *kW0, *kWst, *kACC, *kSFD;
     int k_truth; /* 1: kW0 (and kSFD) hold the current state, the reference-layout fields are stale */
+    /* chain (nsb_chain.cuh): 0 off, 1 three plain kernels, 2 persistent dataflow kernel */
+    int chain_mode;
+    cd *chZ, *chP;     /* L2-resident rings of the persistent kernel */
+    unsigned *chCtr;   /* ticket + per-slab completion counters */
+    int ch_slotZ, ch_slotP, ch_leadG, ch_leadF, ch_ctas, ch_btma;
+    int sm_count;
     long long launches;
     std::set<const void *> *smem_set;
     cudaEvent_t ev0, ev1;
@@ -121,12 +128,17 @@ static int get_field(nsb_ctx *c, int f, void **out) {
 }
 
 template <class K>
-static int ensure_smem(nsb_ctx *c, K kernel, size_t bytes) {
-    if (bytes <= 48 * 1024) return 0;
+static int ensure_smem(nsb_ctx *c, K kernel, size_t bytes, bool max_carveout = false) {
+    if (bytes <= 48 * 1024 && !max_carveout) return 0;
     const void *key = (const void *)kernel;
     if (c->smem_set->count(key)) return 0;
     if (bytes > 227 * 1024) return fail("kernel needs %zu bytes of shared memory (> 227 KB)", bytes);
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (bytes > 48 * 1024)
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    /* measured (round 1): forcing the large carve-out on the L1-reliant kernels (alpha, beta)
+     * costs 5-15 %, so only kernels that ask for it get it */
+    if (max_carveout)
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     c->smem_set->insert(key);
     return 0;
 }
@@ -204,8 +216,30 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->fast = !(getenv("NSB_DISABLE_FAST") && atoi(getenv("NSB_DISABLE_FAST")));
     c->kW0 = c->kWst = c->kACC = c->kSFD = nullptr;
     c->k_truth = 0;
+    c->chZ = c->chP = nullptr;
+    c->chCtr = nullptr;
+    c->chain_mode = 0;
+    if (c->fast && g.X2 == 1024 && c->has_beta && g.ny % NSB_CH_ROWS == 0 && g.Y2 <= NSB_CH_ROWS &&
+        g.Y1 % (NSB_CH_ROWS / g.Y2) == 0) {
+        c->chain_mode = getenv("NSB_CHAIN") ? atoi(getenv("NSB_CHAIN")) : 1;
+    }
+    auto env_int = [](const char *name, int dflt) { return getenv(name) ? atoi(getenv(name)) : dflt; };
+    c->ch_slotZ = env_int("NSB_CHAIN_SLOTS_Z", 8);
+    c->ch_slotP = env_int("NSB_CHAIN_SLOTS_P", 12);
+    c->ch_leadG = env_int("NSB_CHAIN_LEAD_G", 2);
+    c->ch_leadF = env_int("NSB_CHAIN_LEAD_F", 8);
+    c->ch_ctas = env_int("NSB_CHAIN_CTAS", 2) == 2 ? 2 : 1;
+    c->ch_btma = env_int("NSB_CHAIN_BTMA", 1);
+    if (c->ch_leadG < 1) c->ch_leadG = 1;
+    if (c->ch_leadF < 1) c->ch_leadF = 1;
+    if (c->ch_slotZ <= c->ch_leadG) c->ch_slotZ = c->ch_leadG + 1;
+    if (c->ch_slotP <= c->ch_leadF) c->ch_slotP = c->ch_leadF + 1;
+    c->sm_count = 1;
     c->buf_elems = 4 * (g.fsT > g.fsH ? g.fsT : g.fsH);
+    /* plain-kernel chain keeps the packed comb spectra Z (2 x ny*X1 x 1024) in bufB */
+    if (c->chain_mode && (size_t)2 * g.ny * g.X1 * 1024 > c->buf_elems) c->buf_elems = (size_t)2 * g.ny * g.X1 * 1024;
 
+    CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, p->device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaMalloc((void **)&c->bufA, c->buf_elems * sizeof(cd)));
     CK(cudaMalloc((void **)&c->bufB, c->buf_elems * sizeof(cd)));
@@ -270,6 +304,9 @@ extern "C" void nsb_ctx_destroy(nsb_ctx *c) {
     if (c->kWst) cudaFree(c->kWst);
     if (c->kACC) cudaFree(c->kACC);
     if (c->kSFD) cudaFree(c->kSFD);
+    if (c->chZ) cudaFree(c->chZ);
+    if (c->chP) cudaFree(c->chP);
+    if (c->chCtr) cudaFree(c->chCtr);
     cudaFree(c->d_kx); cudaFree(c->d_ky); cudaFree(c->d_kyK); cudaFree(c->d_WY); cudaFree(c->d_WX);
     cudaFree(c->d_sc); cudaFreeHost(c->h_sc);
     if (c->d_force) cudaFree(c->d_force);
@@ -686,6 +723,115 @@ static int launch_gamma(nsb_ctx *c, int mode, const GammaArgs &a) {
     return 0;
 }
 
+/* T (bufA, 4 fields) -> T' (bufB): B, G, F of nsb_chain.cuh */
+static int launch_chain(nsb_ctx *c, bool want_umax) {
+    const NsbGeom &g = c->g;
+    ChainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.T = c->bufA;
+    a.Tp = c->bufB;
+    a.nslab = g.ny / NSB_CH_ROWS;
+    a.GY = NSB_CH_ROWS / g.Y2;
+    a.NQ = NSB_CH_ROWS * g.X1;
+    a.nbatch = (g.X2h + 1 + g.BC - 1) / g.BC; /* every k2 of a comb spectrum is written, also when X1 == 1 */
+    nsb_beta_segs(g.imax, g.X1, g.X2, &a.nd, &a.nm);
+    a.umax_bits = &c->d_sc->umax_bits;
+    const int NP = a.NQ / 2;
+    const int W = (c->chain_mode == 2 && c->ch_ctas == 2) ? (want_umax ? 3 : 4) : (want_umax ? 6 : 8);
+    const size_t tileB = (size_t)2 * NSB_CH_ROWS * (a.nd + a.nm) * g.BC * sizeof(cd);
+    const size_t tileF = tileB / 2;
+    const size_t smemG = NSB_CH_TW_BYTES + (size_t)W * (want_umax ? NSB_CHG_WARP_BYTES(1) : NSB_CHG_WARP_BYTES(0));
+    if (c->chain_mode == 1) {
+        /* Z in bufB, P in bufA (T is dead once B has run), T' back in bufB (Z dead after G) */
+        a.nslotZ = a.nslotP = a.nslab;
+        a.Z = c->bufB;
+        a.P = c->bufA;
+        if (c->ch_btma && 2 * tileB + 64 <= 227 * 1024) {
+            /* persistent, TMA-fed B: one CTA per SM, two shared-memory stages */
+            auto k = k_chain_B_tma;
+            const size_t smemB = 2 * tileB + 64;
+            if (ensure_smem(c, k, smemB, true)) return -1;
+            prof_pre(c, PK_BETA_INV);
+            NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), smemB, c->stream, g, a);
+            prof_post(c);
+            CKL();
+            c->launches++;
+        } else {
+            auto k = k_chain_B;
+            if (ensure_smem(c, k, tileB, true)) return -1;
+            prof_pre(c, PK_BETA_INV);
+            NSB_LAUNCH(k, dim3(a.nbatch, 2, a.nslab), dim3(256), tileB, c->stream, g, a);
+            prof_post(c);
+            CKL();
+            c->launches++;
+        }
+        const dim3 gridG((NP + W - 1) / W, a.nslab);
+        prof_pre(c, PK_GAMMA);
+        if (want_umax) {
+            auto k = k_chain_G<true>;
+            if (ensure_smem(c, k, smemG, true)) return -1;
+            NSB_LAUNCH(k, gridG, dim3(W * 32), smemG, c->stream, g, a);
+        } else {
+            auto k = k_chain_G<false>;
+            if (ensure_smem(c, k, smemG, true)) return -1;
+            NSB_LAUNCH(k, gridG, dim3(W * 32), smemG, c->stream, g, a);
+        }
+        prof_post(c);
+        CKL();
+        c->launches++;
+        {
+            auto k = k_chain_F;
+            if (ensure_smem(c, k, tileF, true)) return -1;
+            prof_pre(c, PK_BETA_FWD);
+            NSB_LAUNCH(k, dim3(a.nbatch, a.nslab), dim3(256), tileF, c->stream, g, a);
+            prof_post(c);
+            CKL();
+            c->launches++;
+        }
+        return 0;
+    }
+    /* persistent dataflow kernel over L2-resident rings */
+    a.nslotZ = c->ch_slotZ < a.nslab ? c->ch_slotZ : a.nslab;
+    a.nslotP = c->ch_slotP < a.nslab ? c->ch_slotP : a.nslab;
+    a.leadG = c->ch_leadG;
+    a.leadF = c->ch_leadF;
+    if (a.nslotZ <= a.leadG) a.leadG = a.nslotZ > 1 ? a.nslotZ - 1 : 1;
+    if (a.nslotP <= a.leadF) a.leadF = a.nslotP > 1 ? a.nslotP - 1 : 1;
+    if (a.nslotZ <= a.leadG || a.nslotP <= a.leadF) { /* single-slab grids: no ring reuse can occur */
+        a.nslotZ = a.leadG + 1;
+        a.nslotP = a.leadF + 1;
+    }
+    const size_t ctr_n = 1 + 3 * (size_t)a.nslab;
+    if (!c->chZ) {
+        CK(cudaMalloc((void **)&c->chZ, (size_t)(c->ch_slotZ + 1) * 2 * a.NQ * 1024 * sizeof(cd)));
+        CK(cudaMalloc((void **)&c->chP, (size_t)(c->ch_slotP + 1) * NP * 1024 * sizeof(cd)));
+        CK(cudaMalloc((void **)&c->chCtr, ctr_n * sizeof(unsigned)));
+    }
+    a.Z = c->chZ;
+    a.P = c->chP;
+    a.ctr = c->chCtr;
+    CK(cudaMemsetAsync(c->chCtr, 0, ctr_n * sizeof(unsigned), c->stream));
+    size_t smem = smemG;
+    if (NSB_CH_TW_BYTES + tileB > smem) smem = NSB_CH_TW_BYTES + tileB;
+    prof_pre(c, PK_GAMMA);
+#define NSB_CHAIN_LAUNCH(UM, WW, MB)                                                            \
+    {                                                                                           \
+        auto k = k_chain<UM, WW, MB>;                                                           \
+        if (ensure_smem(c, k, smem, true)) return -1;                                           \
+        NSB_LAUNCH(k, dim3(c->sm_count * MB), dim3(WW * 32), smem, c->stream, g, a);            \
+    }
+    if (c->ch_ctas == 2) {
+        if (want_umax) NSB_CHAIN_LAUNCH(true, 3, 2) else NSB_CHAIN_LAUNCH(false, 4, 2)
+    } else {
+        if (want_umax) NSB_CHAIN_LAUNCH(true, 6, 1) else NSB_CHAIN_LAUNCH(false, 8, 1)
+    }
+#undef NSB_CHAIN_LAUNCH
+    prof_post(c);
+    CKL();
+    c->launches++;
+    return 0;
+}
+
 /* spectral (masked) -> physical for nf fields produced by alpha source `mode` */
 static int inverse_fields(nsb_ctx *c, int mode, int nf, const cd *const *src, double *const *phys_out,
                           bool want_umax, bool want_sums) {
@@ -982,6 +1128,29 @@ extern "C" int nsb_rk4_step(nsb_ctx *c, double dt) {
             ai.nf = 4; ai.src[0] = src;
             ai.out = c->bufA; ai.out_fs = g.fsT; ai.out_pitch = g.PT;
             if (launch_alpha_inv(c, NSB_SRC_STEP, ai)) return -1;
+        }
+        if (c->chain_mode) {
+            /* T (bufA) -> T' (bufB) in one persistent kernel (or three plain ones) */
+            if (launch_chain(c, want_umax)) return -1;
+            if (want_umax && launch_cfl(c)) return -1;
+            if (afast) {
+                AlphaFastArgs fa;
+                memset(&fa, 0, sizeof(fa));
+                fa.in = c->bufB; fa.in_pitch = g.PT;
+                fa.out = c->bufA; fa.out_fs = g.fsT; fa.out_pitch = g.PT; fa.rk = rk;
+                if (launch_alpha1024(c, true, stage < 4, fa)) return -1;
+            } else {
+                af.in = c->bufB;
+                af.in_pitch = g.PT;
+                if (launch_alpha_fwd(c, NSB_EPI_RK, af)) return -1;
+                if (c->masked_nonzero) {
+                    auto k = k_rk_masked;
+                    NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 0, c->stream, g, rk);
+                    CKL();
+                    c->launches++;
+                }
+            }
+            continue;
         }
         const cd *H = c->bufA;
         cd *Hp = c->bufB;

@@ -22,6 +22,37 @@
 
 typedef double2 cd; /* complex double: x = re, y = im */
 
+/*
+ * Inter-CTA dataflow helpers of the persistent chain kernel (nsb_chain.cuh): L2-only loads
+ * for data another CTA of the same launch produced (L1 is not coherent), acquire polling and
+ * release signalling of completion counters in global memory.
+ */
+#ifdef NSB_EMULATE
+static inline cd nsb_ldcg(const cd *p) { return *p; }
+static inline cd nsb_ldcs(const cd *p) { return *p; }
+static inline void nsb_stcs(cd *p, cd v) { *p = v; }
+static inline void nsb_prefetch_l2(const void *) {}
+static inline unsigned nsb_ld_acquire(const unsigned *p) { return *p; }
+static inline void nsb_red_release(unsigned *p, unsigned v) { *p += v; }
+static inline void nsb_backoff() { nsbemu::yield(); }
+#else
+__device__ __forceinline__ cd nsb_ldcg(const cd *p) { return __ldcg(p); }
+/* read-once / write-once streams (evict-first) so they do not displace the L2-resident rings */
+__device__ __forceinline__ cd nsb_ldcs(const cd *p) { return __ldcs(p); }
+__device__ __forceinline__ void nsb_stcs(cd *p, cd v) { __stcs(p, v); }
+__device__ __forceinline__ void nsb_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ unsigned nsb_ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void nsb_red_release(unsigned *p, unsigned v) {
+    __threadfence();
+    atomicAdd(p, v);
+}
+__device__ __forceinline__ void nsb_backoff() { __nanosleep(64); }
+#endif
+
 /* correctly rounded FP64 reciprocal (MUFU.RCP64H + Newton, inlined: no division subroutine) */
 #ifdef NSB_EMULATE
 static inline double nsb_drcp(double a) { return 1.0 / a; }
@@ -38,7 +69,10 @@ __device__ __forceinline__ double nsb_drcp(double a) { return __drcp_rn(a); }
 typedef unsigned long long nsb_mbar_t;
 /* emulated mbarrier: low 32 bits = completed phases, high 32 bits = pending tx bytes */
 static inline void nsb_mbar_init(nsb_mbar_t *bar, int) { *bar = 0; }
-static inline void nsb_mbar_expect_tx(nsb_mbar_t *bar, unsigned bytes) { *bar += (unsigned long long)bytes << 32; }
+static inline void nsb_mbar_expect_tx(nsb_mbar_t *bar, unsigned bytes) {
+    *bar += (unsigned long long)bytes << 32;
+    if (bytes == 0) *bar += 1; /* arrive.expect_tx with nothing pending completes the phase */
+}
 static inline void nsb_bulk_g2s(void *dst, const void *src, unsigned bytes, nsb_mbar_t *bar) {
     memcpy(dst, src, bytes);
     *bar -= (unsigned long long)bytes << 32;

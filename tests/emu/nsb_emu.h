@@ -92,6 +92,7 @@ static inline unsigned long long atomicMax(unsigned long long *a, unsigned long 
 }
 static inline double atomicAdd(double *a, double v) { double o = *a; *a = o + v; return o; }
 static inline int atomicAdd(int *a, int v) { int o = *a; *a = o + v; return o; }
+static inline unsigned atomicAdd(unsigned *a, unsigned v) { unsigned o = *a; *a = o + v; return o; }
 static inline unsigned atomicOr(unsigned *a, unsigned v) { unsigned o = *a; *a = o | v; return o; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
@@ -105,7 +106,10 @@ typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
+enum { cudaSharedmemCarveoutMaxShared = 100 };
+enum { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 2; return 0; }
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
 static inline const char *cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaGetLastError() { return 0; }

@@ -71,3 +71,52 @@ def test_emu_alpha1024_fused_path(nsb, emu_lib, oracles, nx, ny, plan, hv, forci
 
 def test_emu_alpha1024_free_running_with_diagnostics(nsb, emu_lib, oracles):
     pc.check_free_running(nsb, emu_lib, oracles, best_oracle_kind(oracles), 16, 1024, 6, every=3, hv=HV)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("nx,ny,plan", [
+    (2048, 32, dict(x2=1024, y1=16)),          # X1 = 2, Y2 = 2: 8 y1 values per slab, 2 slabs
+    (4096, 16, dict(x2=1024, y1=4)),           # X1 = 4, Y2 = 4: one slab
+    (1024, 32, dict(x2=1024, y1=2)),           # X1 = 1, Y2 = 16: comb pairs are row pairs
+])
+def test_emu_chain(nsb, emu_lib, oracles, monkeypatch, mode, nx, ny, plan):
+    """X2 == 1024 with a beta split selects the B/G/F chain (nsb_chain.cuh): mode 1 = three
+    plain kernels, mode 2 = the persistent dataflow kernel over ring buffers."""
+    monkeypatch.setenv("NSB_CHAIN", str(mode))
+    pc.check_per_step(nsb, emu_lib, oracles, best_oracle_kind(oracles), nx, ny, 2, hv=HV,
+                      forcing=dict(kind="white"), **plan)
+
+
+def test_emu_chain_ring_reuse(nsb, emu_lib, oracles, monkeypatch):
+    """4 slabs through 2-slot rings: slot reuse and the completion-counter waits."""
+    monkeypatch.setenv("NSB_CHAIN", "2")
+    monkeypatch.setenv("NSB_CHAIN_SLOTS_Z", "2")
+    monkeypatch.setenv("NSB_CHAIN_SLOTS_P", "2")
+    monkeypatch.setenv("NSB_CHAIN_LEAD_G", "1")
+    monkeypatch.setenv("NSB_CHAIN_LEAD_F", "1")
+    pc.check_per_step(nsb, emu_lib, oracles, best_oracle_kind(oracles), 2048, 64, 2, hv=HV,
+                      forcing=dict(kind="white"), x2=1024, y1=32)
+
+
+def test_emu_chain_matches_plain_kernels(nsb, emu_lib, monkeypatch):
+    """Plain and persistent chain run the same item code: bit-identical. Against the separate
+    beta/gamma kernels only the Hermitian packing differs (psi_x + i omega_y instead of
+    psi_x + i psi_y), i.e. rounding-level differences."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    nx, ny = 2048, 32
+    w = np.zeros((ny, nx // 2 + 1), dtype=np.complex128)
+    w[:, :40] = 0.01 * (rng.standard_normal((ny, 40)) + 1j * rng.standard_normal((ny, 40)))
+    w[0, 0] = 0
+    out = {}
+    for mode in (0, 1, 2):
+        monkeypatch.setenv("NSB_CHAIN", str(mode))
+        c = nsb.NsbContext(nx, ny, Re=500.0, lib=emu_lib, x2=1024, y1=16)
+        c.upload(nsb.OMEGA_HAT, w)
+        c.apply_dealiasing(nsb.OMEGA_HAT)
+        c.step(0.0)
+        out[mode] = (c.download(nsb.OMEGA_HAT), c.state()[0])
+        c.close()
+    assert np.array_equal(out[1][0], out[2][0]) and out[1][1] == out[2][1]
+    assert pc.rel(out[1][0], out[0][0]) < 1e-14
+    assert abs(out[1][1] - out[0][1]) <= 1e-15 * out[0][1]

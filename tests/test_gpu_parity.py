@@ -91,3 +91,45 @@ def test_large_size_properties_16384(nsb, cuda_lib):
     assert 0 < d1["energy"] < d0["energy"]
     assert 0 < d1["enstrophy"] < d0["enstrophy"]
     c.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("n,steps", [(2048, 3), (4096, 2)])
+def test_step_chain_modes(nsb, cuda_lib, oracles, monkeypatch, mode, n, steps):
+    """B/G/F chain (nsb_chain.cuh): three plain kernels (1) and the persistent dataflow
+    kernel over L2-resident rings (2, the default) against the oracle."""
+    monkeypatch.setenv("NSB_CHAIN", str(mode))
+    pc.check_per_step(nsb, cuda_lib, oracles, best_oracle_kind(oracles), n, n, steps, hv=HV,
+                      forcing=dict(kind="white"), Re=1e4)
+
+
+def test_chain_persistent_equals_plain_8192(nsb, cuda_lib, monkeypatch):
+    """Ring reuse and counter waits at scale: the persistent kernel must reproduce the plain
+    kernels bit for bit (same item code, different schedule), also with tiny rings."""
+    n = 8192
+    rng = np.random.default_rng(11)
+    w = np.zeros((n, n // 2 + 1), dtype=np.complex128)
+    kk = 96
+    blk = rng.standard_normal((2 * kk + 1, kk + 1)) + 1j * rng.standard_normal((2 * kk + 1, kk + 1))
+    w[(np.arange(-kk, kk + 1) % n)[:, None], np.arange(kk + 1)[None, :]] = 0.02 * blk
+    w[0, 0] = 0.0
+    col = w[:, 0].copy()
+    w[:, 0] = 0.5 * (col + np.conj(col[(-np.arange(n)) % n]))
+    out = []
+    for env in (dict(NSB_CHAIN="1"), dict(NSB_CHAIN="2"),
+                dict(NSB_CHAIN="2", NSB_CHAIN_SLOTS_Z="2", NSB_CHAIN_LEAD_G="1", NSB_CHAIN_SLOTS_P="2",
+                     NSB_CHAIN_LEAD_F="1")):
+        for k in ("NSB_CHAIN", "NSB_CHAIN_SLOTS_Z", "NSB_CHAIN_LEAD_G", "NSB_CHAIN_SLOTS_P", "NSB_CHAIN_LEAD_F"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c = nsb.NsbContext(n, n, Re=1e4, lib=cuda_lib)
+        c.upload(nsb.OMEGA_HAT, w)
+        c.set_hyperviscosity(**HV)
+        for _ in range(3):
+            c.step(0.0)
+        out.append((c.download(nsb.OMEGA_HAT), c.state()[0]))
+        c.close()
+    for o in out[1:]:
+        assert np.array_equal(o[0], out[0][0])
+        assert o[1] == out[0][1]
