@@ -259,7 +259,8 @@ __device__ __forceinline__ void chain_G_item(const ChainArgs &a, unsigned char *
 /* ------------------------------------------------------------------ F items */
 
 template <int X1>
-__device__ __forceinline__ void chain_F_step1(const NsbGeom &g, const ChainArgs &a, cd *tile, int slot, int kb) {
+__device__ __forceinline__ void chain_F_step1(const NsbGeom &g, const ChainArgs &a, cd *tile, int slot, int kb,
+                                              const cd *twtab) {
     const int nseg = a.nd + a.nm;
     const int NP = a.NQ >> 1;
     for (int w = threadIdx.x; w < NSB_CH_ROWS * g.BC; w += blockDim.x) {
@@ -279,8 +280,8 @@ __device__ __forceinline__ void chain_F_step1(const NsbGeom &g, const ChainArgs 
                     const cd Pk = nsb_ldcg(&pr[k2]), Q = nsb_ldcg(&pr[km]);
                     const cd e = cmk(0.5 * (Pk.x + Q.x), 0.5 * (Pk.y - Q.y));
                     const cd o = cmk(0.5 * (Pk.y + Q.y), -0.5 * (Pk.x - Q.x));
-                    x[2 * i] = cmul(e, __ldg(&g.WX[(size_t)k2 * (2 * i)]));
-                    x[2 * i + 1] = cmul(o, __ldg(&g.WX[(size_t)k2 * (2 * i + 1)]));
+                    x[2 * i] = cmul(e, twtab ? twtab[cc * X1 + 2 * i] : __ldg(&g.WX[(size_t)k2 * (2 * i)]));
+                    x[2 * i + 1] = cmul(o, twtab ? twtab[cc * X1 + 2 * i + 1] : __ldg(&g.WX[(size_t)k2 * (2 * i + 1)]));
                 }
             }
             nsb_dft<X1, false>(x);
@@ -324,12 +325,15 @@ __device__ __forceinline__ void chain_F_step2(const NsbGeom &g, const ChainArgs 
 __device__ __forceinline__ void chain_F_item(const NsbGeom &g, const ChainArgs &a, cd *tile, int slab, int slot,
                                              int batch) {
     const int kb = batch * g.BC;
+    /* measured: staging the x twiddles in shared memory (as B does) costs F more in the extra
+     * barrier than the L1/L2 twiddle loads do */
+    const cd *twtab = nullptr;
     switch (g.X1) {
-        case 1: chain_F_step1<1>(g, a, tile, slot, kb); break;
-        case 2: chain_F_step1<2>(g, a, tile, slot, kb); break;
-        case 4: chain_F_step1<4>(g, a, tile, slot, kb); break;
-        case 8: chain_F_step1<8>(g, a, tile, slot, kb); break;
-        default: chain_F_step1<16>(g, a, tile, slot, kb); break;
+        case 1: chain_F_step1<1>(g, a, tile, slot, kb, twtab); break;
+        case 2: chain_F_step1<2>(g, a, tile, slot, kb, twtab); break;
+        case 4: chain_F_step1<4>(g, a, tile, slot, kb, twtab); break;
+        case 8: chain_F_step1<8>(g, a, tile, slot, kb, twtab); break;
+        default: chain_F_step1<16>(g, a, tile, slot, kb, twtab); break;
     }
     __syncthreads();
     switch (g.Y2) {
@@ -342,6 +346,7 @@ __device__ __forceinline__ void chain_F_item(const NsbGeom &g, const ChainArgs &
 }
 
 /* ------------------------------------------------ B, TMA-fed and persistent */
+/* requires NSB_CH_ROWS*BC*16 bytes per box row block, i.e. BC*2 doubles <= 256 and 16 rows */
 
 /*
  * Valid part of column segment `seg` for the k2 batch starting at kb, in ASCENDING memory
@@ -370,32 +375,26 @@ __device__ __forceinline__ void chain_seg_range(const NsbGeom &g, int nd, int se
     }
 }
 
-/* TMA bulk copies (cp.async.bulk, one 16*cnt-byte row segment per copy, issued by all threads)
- * of the raw input of item (slab, pp, batch) into `tile`; completion on `bar`. */
-__device__ __forceinline__ void chain_B_issue(const NsbGeom &g, const ChainArgs &a, cd *tile, nsb_mbar_t *bar, int slab,
-                                              int pp, int kb) {
+/*
+ * TMA tensor copies of the raw input of item (slab, pp, batch): one 16-row x BC-column box
+ * (4 KB) per (field, segment) through the tensor map of T (rows = 4*ny, pitch PT), landing
+ * at tile[(fi*nseg + seg)*16 + row][pos]. Columns outside the retained set come back as
+ * zeros or as neighbouring retained columns; step 1 masks them by range. Completion on `bar`.
+ */
+__device__ __forceinline__ void chain_B_issue(const NsbGeom &g, const ChainArgs &a, const nsb_tmap *tmT, cd *tile,
+                                              nsb_mbar_t *bar, int slab, int pp, int kb) {
     const int nseg = a.nd + a.nm;
-    const int rows = 2 * NSB_CH_ROWS; /* (field, gy, j2) */
     if (threadIdx.x == 0) {
-        unsigned total = 0;
-        for (int seg = 0; seg < nseg; ++seg) {
-            int p0, cnt, c0;
-            chain_seg_range(g, a.nd, seg, kb, &p0, &cnt, &c0);
-            total += (unsigned)cnt * 16u * (unsigned)rows;
-        }
         nsb_fence_proxy_async();
-        nsb_mbar_expect_tx(bar, total);
+        nsb_mbar_expect_tx(bar, (unsigned)(2 * nseg) * (unsigned)(NSB_CH_ROWS * g.BC * 16));
     }
     __syncthreads();
-    const int fa = pp == 0 ? 0 : 1, fb = pp == 0 ? 3 : 2;
-    for (int w = threadIdx.x; w < rows * nseg; w += blockDim.x) {
-        const int row = w / nseg, seg = w - row * nseg; /* row = fi*16 + gy*Y2 + j2 */
-        int p0, cnt, c0;
-        chain_seg_range(g, a.nd, seg, kb, &p0, &cnt, &c0);
-        if (cnt <= 0) continue;
-        const int fi = row / NSB_CH_ROWS, rr = row - fi * NSB_CH_ROWS;
-        const cd *src = a.T + (size_t)(fi ? fb : fa) * g.fsT + (size_t)(slab * NSB_CH_ROWS + rr) * g.PT + c0;
-        nsb_bulk_g2s(tile + (size_t)(row * nseg + seg) * g.BC + p0, src, (unsigned)cnt * 16u, bar);
+    if ((int)threadIdx.x < 2 * nseg) {
+        const int fi = threadIdx.x / nseg, seg = threadIdx.x - fi * nseg;
+        const int f = pp == 0 ? (fi ? 3 : 0) : (fi ? 2 : 1);
+        const int col0 = (seg < a.nd) ? seg * g.X2 + kb : (seg - a.nd) * g.X2 + g.X2 - kb - (g.BC - 1);
+        nsb_tma_2d_g2s(tile + (size_t)(fi * nseg + seg) * NSB_CH_ROWS * g.BC, tmT, 2 * col0,
+                       f * g.ny + slab * NSB_CH_ROWS, bar);
     }
 }
 
@@ -412,40 +411,41 @@ __device__ __forceinline__ void chain_B2_step1(const NsbGeom &g, const ChainArgs
         const int seg = r / g.BC, pos = r - seg * g.BC;
         int p0, cnt, c0;
         chain_seg_range(g, a.nd, seg, kb, &p0, &cnt, &c0);
-        cd *col = tile + (size_t)((fi * NSB_CH_ROWS + gy * Y2) * nseg + seg) * g.BC + pos;
-        const size_t rs = (size_t)nseg * g.BC;
+        cd *col = tile + (size_t)((fi * nseg + seg) * NSB_CH_ROWS + gy * Y2) * g.BC + pos;
         cd x[Y2];
         if (pos >= p0 && pos < p0 + cnt) {
 #pragma unroll
-            for (int j2 = 0; j2 < Y2; ++j2) x[j2] = col[j2 * rs];
+            for (int j2 = 0; j2 < Y2; ++j2) x[j2] = col[j2 * g.BC];
             nsb_dft<Y2, true>(x);
         } else {
 #pragma unroll
             for (int j2 = 0; j2 < Y2; ++j2) x[j2] = cmk(0.0, 0.0);
         }
 #pragma unroll
-        for (int y2 = 0; y2 < Y2; ++y2) col[y2 * rs] = x[y2];
+        for (int y2 = 0; y2 < Y2; ++y2) col[y2 * g.BC] = x[y2];
     }
 }
 
 /* gather for tiles in memory order (mirror segments reversed) */
 template <int X1>
-__device__ __forceinline__ void chain_gather_mo(cd (&x)[X1], const cd *tile, int row, int nseg, int nd, int nm, int BC,
-                                                int cc) {
+__device__ __forceinline__ void chain_gather_mo(cd (&x)[X1], const cd *tile, int fi, int r, int nseg, int nd, int nm,
+                                                int BC, int cc) {
 #pragma unroll
     for (int k1 = 0; k1 < X1; ++k1) {
         if (X1 == 1 || k1 < X1 / 2) {
-            x[k1] = (k1 < nd) ? tile[(size_t)(row * nseg + k1) * BC + cc] : cmk(0.0, 0.0);
+            x[k1] = (k1 < nd) ? tile[(size_t)((fi * nseg + k1) * NSB_CH_ROWS + r) * BC + cc] : cmk(0.0, 0.0);
         } else {
             const int kp = X1 - 1 - k1;
-            x[k1] = (kp < nm) ? cconj(tile[(size_t)(row * nseg + nd + kp) * BC + (BC - 1 - cc)]) : cmk(0.0, 0.0);
+            x[k1] = (kp < nm) ? cconj(tile[(size_t)((fi * nseg + nd + kp) * NSB_CH_ROWS + r) * BC + (BC - 1 - cc)])
+                              : cmk(0.0, 0.0);
         }
     }
 }
 
+/* twtab (nullable): shared-memory copy of the x twiddles of this batch, twtab[cc*X1 + x1] */
 template <int X1, bool MO>
 __device__ __forceinline__ void chain_B_step2x(const NsbGeom &g, const ChainArgs &a, const cd *tile, int slot, int pp,
-                                               int kb) {
+                                               int kb, const cd *twtab) {
     const int nseg = a.nd + a.nm;
     for (int w = threadIdx.x; w < NSB_CH_ROWS * g.BC; w += blockDim.x) {
         const int r = w / g.BC, cc = w - r * g.BC;
@@ -453,8 +453,8 @@ __device__ __forceinline__ void chain_B_step2x(const NsbGeom &g, const ChainArgs
         if (k2 > g.X2h) continue;
         cd A[X1], B[X1];
         if (MO) {
-            chain_gather_mo<X1>(A, tile, r, nseg, a.nd, a.nm, g.BC, cc);
-            chain_gather_mo<X1>(B, tile, NSB_CH_ROWS + r, nseg, a.nd, a.nm, g.BC, cc);
+            chain_gather_mo<X1>(A, tile, 0, r, nseg, a.nd, a.nm, g.BC, cc);
+            chain_gather_mo<X1>(B, tile, 1, r, nseg, a.nd, a.nm, g.BC, cc);
         } else {
             chain_gather<X1>(A, tile, r, nseg, a.nd, a.nm, g.BC, cc);
             chain_gather<X1>(B, tile, NSB_CH_ROWS + r, nseg, a.nd, a.nm, g.BC, cc);
@@ -470,7 +470,7 @@ __device__ __forceinline__ void chain_B_step2x(const NsbGeom &g, const ChainArgs
         for (int x1 = 0; x1 < X1; ++x1) {
             cd av = A[x1], bv = B[x1];
             if (X1 > 1) {
-                const cd tw = __ldg(&g.WX[(size_t)k2 * x1]);
+                const cd tw = twtab ? twtab[cc * X1 + x1] : __ldg(&g.WX[(size_t)k2 * x1]);
                 av = cmulc(av, tw);
                 bv = cmulc(bv, tw);
             }
@@ -491,13 +491,15 @@ __device__ __forceinline__ void chain_B_step2x(const NsbGeom &g, const ChainArgs
  * (item = (slab, pp, batch), batch fastest). Two shared-memory stages: while the CTA
  * transforms the tile of item n, the bulk copies of item n+1 are in flight, so HBM latency
  * is off the critical path with one CTA per SM.
- * smem: 2 stages x (2*16*nseg*BC complex) + 2 mbarriers.
+ * smem: 2 stages x (2*16*nseg*BC complex) + 2 mbarriers (+128 B alignment slack).
  */
-__global__ void __launch_bounds__(256, 1) k_chain_B_tma(NsbGeom g, ChainArgs a) {
-    NSB_DYN_SMEM(cd, smem);
+__global__ void __launch_bounds__(256, 1) k_chain_B_tma(NsbGeom g, ChainArgs a, const NSB_GRID_CONSTANT nsb_tmap tmT) {
+    NSB_DYN_SMEM(cd, smem_raw);
+    cd *smem = reinterpret_cast<cd *>((reinterpret_cast<size_t>(smem_raw) + 127) & ~(size_t)127);
     const int nseg = a.nd + a.nm;
     const size_t tile_elems = (size_t)2 * NSB_CH_ROWS * nseg * g.BC;
     nsb_mbar_t *bars = reinterpret_cast<nsb_mbar_t *>(smem + 2 * tile_elems);
+    cd *twtab = smem + 2 * tile_elems + 4; /* BC * X1 x twiddles of the current batch */
     if (threadIdx.x == 0) {
         nsb_mbar_init(&bars[0], 1);
         nsb_mbar_init(&bars[1], 1);
@@ -508,14 +510,14 @@ __global__ void __launch_bounds__(256, 1) k_chain_B_tma(NsbGeom g, ChainArgs a) 
     int item = blockIdx.x;
     if (item < nitems) {
         const int slab = item / (2 * a.nbatch), rem = item - slab * 2 * a.nbatch;
-        chain_B_issue(g, a, smem, &bars[0], slab, rem / a.nbatch, (rem % a.nbatch) * g.BC);
+        chain_B_issue(g, a, &tmT, smem, &bars[0], slab, rem / a.nbatch, (rem % a.nbatch) * g.BC);
     }
     for (int n = 0; item < nitems; ++n, item += gridDim.x) {
         const int st = n & 1;
         const int next = item + gridDim.x;
         if (next < nitems) {
             const int slab = next / (2 * a.nbatch), rem = next - slab * 2 * a.nbatch;
-            chain_B_issue(g, a, smem + (size_t)(st ^ 1) * tile_elems, &bars[st ^ 1], slab, rem / a.nbatch,
+            chain_B_issue(g, a, &tmT, smem + (size_t)(st ^ 1) * tile_elems, &bars[st ^ 1], slab, rem / a.nbatch,
                           (rem % a.nbatch) * g.BC);
         }
         nsb_mbar_wait(&bars[st], phase[st]);
@@ -523,6 +525,10 @@ __global__ void __launch_bounds__(256, 1) k_chain_B_tma(NsbGeom g, ChainArgs a) 
         cd *tile = smem + (size_t)st * tile_elems;
         const int slab = item / (2 * a.nbatch), rem = item - slab * 2 * a.nbatch;
         const int pp = rem / a.nbatch, kb = (rem % a.nbatch) * g.BC;
+        for (int w = threadIdx.x; w < g.BC * g.X1; w += blockDim.x) {
+            const int cc = w / g.X1, x1 = w - cc * g.X1;
+            twtab[w] = (kb + cc <= g.X2h) ? __ldg(&g.WX[(size_t)(kb + cc) * x1]) : cmk(1.0, 0.0);
+        }
         switch (g.Y2) {
             case 1: chain_B2_step1<1>(g, a, tile, kb); break;
             case 2: chain_B2_step1<2>(g, a, tile, kb); break;
@@ -533,11 +539,11 @@ __global__ void __launch_bounds__(256, 1) k_chain_B_tma(NsbGeom g, ChainArgs a) 
         __syncthreads();
         const int slot = slab % a.nslotZ;
         switch (g.X1) {
-            case 1: chain_B_step2x<1, true>(g, a, tile, slot, pp, kb); break;
-            case 2: chain_B_step2x<2, true>(g, a, tile, slot, pp, kb); break;
-            case 4: chain_B_step2x<4, true>(g, a, tile, slot, pp, kb); break;
-            case 8: chain_B_step2x<8, true>(g, a, tile, slot, pp, kb); break;
-            default: chain_B_step2x<16, true>(g, a, tile, slot, pp, kb); break;
+            case 1: chain_B_step2x<1, true>(g, a, tile, slot, pp, kb, twtab); break;
+            case 2: chain_B_step2x<2, true>(g, a, tile, slot, pp, kb, twtab); break;
+            case 4: chain_B_step2x<4, true>(g, a, tile, slot, pp, kb, twtab); break;
+            case 8: chain_B_step2x<8, true>(g, a, tile, slot, pp, kb, twtab); break;
+            default: chain_B_step2x<16, true>(g, a, tile, slot, pp, kb, twtab); break;
         }
         __syncthreads(); /* the tile is free for the copies of item n+2 */
     }

@@ -76,6 +76,8 @@ struct nsb_ctx {
     cd *chZ, *chP;     /* L2-resident rings of the persistent kernel */
     unsigned *chCtr;   /* ticket + per-slab completion counters */
     int ch_slotZ, ch_slotP, ch_leadG, ch_leadF, ch_ctas, ch_btma;
+    nsb_tmap tmT; /* tensor map of T in bufA (TMA-fed B) */
+    int tmT_ok;
     int sm_count;
     long long launches;
     std::set<const void *> *smem_set;
@@ -217,6 +219,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->kW0 = c->kWst = c->kACC = c->kSFD = nullptr;
     c->k_truth = 0;
     c->chZ = c->chP = nullptr;
+    c->tmT_ok = 0;
     c->chCtr = nullptr;
     c->chain_mode = 0;
     if (c->fast && g.X2 == 1024 && c->has_beta && g.ny % NSB_CH_ROWS == 0 && g.Y2 <= NSB_CH_ROWS &&
@@ -723,6 +726,43 @@ static int launch_gamma(nsb_ctx *c, int mode, const GammaArgs &a) {
     return 0;
 }
 
+/* 2-D FP64 tensor map over a pitched array: dim0 doubles per row, dim1 rows, pitch in bytes,
+ * box0 x box1 tile (nsb_platform.h: nsb_tma_2d_g2s). The driver entry point is resolved at
+ * run time so the library has no link-time dependency on libcuda. */
+static int make_tmap_2d(nsb_tmap *out, const void *base, size_t dim0, size_t dim1, size_t pitch_bytes, int box0,
+                        int box1) {
+#ifdef NSB_EMULATE
+    out->base = (const double *)base;
+    out->dim0 = (long long)dim0;
+    out->dim1 = (long long)dim1;
+    out->stride1 = (long long)pitch_bytes;
+    out->box0 = box0;
+    out->box1 = box1;
+    return 0;
+#else
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available");
+        encode = (encode_fn)fn;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+    const cuuint64_t gstr[1] = {(cuuint64_t)pitch_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+#endif
+}
+
 /* T (bufA, 4 fields) -> T' (bufB): B, G, F of nsb_chain.cuh */
 static int launch_chain(nsb_ctx *c, bool want_umax) {
     const NsbGeom &g = c->g;
@@ -739,20 +779,27 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
     const int NP = a.NQ / 2;
     const int W = (c->chain_mode == 2 && c->ch_ctas == 2) ? (want_umax ? 3 : 4) : (want_umax ? 6 : 8);
     const size_t tileB = (size_t)2 * NSB_CH_ROWS * (a.nd + a.nm) * g.BC * sizeof(cd);
-    const size_t tileF = tileB / 2;
+    const size_t twtab = (size_t)g.BC * g.X1 * sizeof(cd);
+    const size_t tileF = tileB / 2 + twtab;
     const size_t smemG = NSB_CH_TW_BYTES + (size_t)W * (want_umax ? NSB_CHG_WARP_BYTES(1) : NSB_CHG_WARP_BYTES(0));
     if (c->chain_mode == 1) {
         /* Z in bufB, P in bufA (T is dead once B has run), T' back in bufB (Z dead after G) */
         a.nslotZ = a.nslotP = a.nslab;
         a.Z = c->bufB;
         a.P = c->bufA;
-        if (c->ch_btma && 2 * tileB + 64 <= 227 * 1024) {
+        if (c->ch_btma && 2 * tileB + 64 + 128 + twtab <= 227 * 1024 && 2 * g.BC <= 256) {
             /* persistent, TMA-fed B: one CTA per SM, two shared-memory stages */
             auto k = k_chain_B_tma;
-            const size_t smemB = 2 * tileB + 64;
+            const size_t smemB = 2 * tileB + 64 + 128 + twtab;
             if (ensure_smem(c, k, smemB, true)) return -1;
+            if (!c->tmT_ok) {
+                if (make_tmap_2d(&c->tmT, c->bufA, (size_t)2 * g.PT, (size_t)4 * g.ny, (size_t)g.PT * sizeof(cd),
+                                 2 * g.BC, NSB_CH_ROWS))
+                    return -1;
+                c->tmT_ok = 1;
+            }
             prof_pre(c, PK_BETA_INV);
-            NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), smemB, c->stream, g, a);
+            NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), smemB, c->stream, g, a, c->tmT);
             prof_post(c);
             CKL();
             c->launches++;
@@ -813,6 +860,7 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
     CK(cudaMemsetAsync(c->chCtr, 0, ctr_n * sizeof(unsigned), c->stream));
     size_t smem = smemG;
     if (NSB_CH_TW_BYTES + tileB > smem) smem = NSB_CH_TW_BYTES + tileB;
+    if (NSB_CH_TW_BYTES + tileF > smem) smem = NSB_CH_TW_BYTES + tileF;
     prof_pre(c, PK_GAMMA);
 #define NSB_CHAIN_LAUNCH(UM, WW, MB)                                                            \
     {                                                                                           \

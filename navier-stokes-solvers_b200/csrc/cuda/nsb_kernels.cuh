@@ -989,10 +989,11 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
         }
     }
     __syncthreads();
+    cd x[32];
+    bool prefetched = false;
 #pragma unroll 1
     for (int job = FWD ? 0 : 1; job <= (INV ? 4 : 0); ++job) {
         if (active) {
-            cd x[32];
             if (job == 0) {
 #pragma unroll
                 for (int m = 0; m < 32; ++m) {
@@ -1003,9 +1004,12 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
                 __syncwarp(); /* every lane holds its values before the transpose reuses the slots */
             } else {
                 const int f = job - 1;
-                /* all 32 state loads in flight at once (unconditional: K layout covers every row) */
+                /* all 32 state loads in flight at once (unconditional: K layout covers every row);
+                 * for jobs 2-4 they were issued before the previous job's store phase */
+                if (!prefetched) {
 #pragma unroll
-                for (int m = 0; m < 32; ++m) x[m] = Wre[kbase + lane + 32 * m];
+                    for (int m = 0; m < 32; ++m) x[m] = Wre[kbase + lane + 32 * m];
+                }
 #pragma unroll
                 for (int m = 0; m < 32; ++m) {
                     const int j1 = lane + 32 * m;
@@ -1033,6 +1037,13 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
                     cd v = x[m];
                     if (g.Y2 > 1) v = cmulc(v, cmul(ta, TB[m]));
                     S[nsb_sidx(lane + 32 * m, warp)] = v;
+                }
+                /* registers are free until the next transform: fetch its input now so the
+                 * latency hides behind the barrier and the cooperative store of this tile */
+                if (job < 4) {
+#pragma unroll
+                    for (int m = 0; m < 32; ++m) x[m] = Wre[kbase + lane + 32 * m];
+                    prefetched = true;
                 }
             }
         }

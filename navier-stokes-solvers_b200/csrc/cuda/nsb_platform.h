@@ -119,4 +119,47 @@ __device__ __forceinline__ void nsb_fence_proxy_async() {
 }
 #endif
 
+/*
+ * TMA tiled tensor copies (cp.async.bulk.tensor.2d, SASS UTMALDG): one instruction moves a
+ * box of box1 rows x box0 doubles from a pitched 2-D FP64 array into shared memory, rows
+ * packed back to back; out-of-range coordinates are zero-filled. The descriptor is encoded
+ * on the host (nsb_ctx.cu: make_tmap_2d via cuTensorMapEncodeTiled) and passed to the kernel
+ * as a __grid_constant__ parameter. Under the CPU emulator it is a plain struct and the copy
+ * an immediate strided memcpy.
+ */
+#ifdef NSB_EMULATE
+struct nsb_tmap {
+    const double *base;
+    long long dim0, dim1;     /* extent in doubles / rows */
+    long long stride1;        /* row pitch in bytes */
+    int box0, box1;
+};
+#define NSB_GRID_CONSTANT
+static inline void nsb_tma_2d_g2s(void *dst, const nsb_tmap *m, int c0, int c1, nsb_mbar_t *bar) {
+    double *d = (double *)dst;
+    for (int r = 0; r < m->box1; ++r)
+        for (int e = 0; e < m->box0; ++e) {
+            const long long row = (long long)c1 + r, col = (long long)c0 + e;
+            double v = 0.0;
+            if (row >= 0 && row < m->dim1 && col >= 0 && col < m->dim0)
+                v = *(const double *)((const char *)m->base + row * m->stride1 + col * 8);
+            d[(size_t)r * m->box0 + e] = v;
+        }
+    const unsigned long long bytes = (unsigned long long)m->box0 * m->box1 * 8ull;
+    *bar -= bytes << 32;
+    if ((*bar >> 32) == 0) *bar += 1;
+}
+#else
+#include <cuda.h>
+typedef CUtensorMap nsb_tmap;
+#define NSB_GRID_CONSTANT __grid_constant__
+__device__ __forceinline__ void nsb_tma_2d_g2s(void *dst, const nsb_tmap *map, int c0, int c1, nsb_mbar_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            nsb_smem_addr(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(nsb_smem_addr(bar))
+        : "memory");
+}
+#endif
+
 #endif
