@@ -149,6 +149,30 @@ int nsb_timer_stop(nsb_ctx *c, float *ms);
  * 0 alpha_inv, 1 beta_inv, 2 gamma, 3 beta_fwd, 4 alpha_fwd, 5 other. */
 int nsb_profile_begin(nsb_ctx *c);
 int nsb_profile_end(nsb_ctx *c, double ms[6], int count[6]);
+/*
+ * Slab decomposition over the devices of one NVSwitch domain (the reference
+ * has no distributed code: /root/reference/src/spectral/spectral_initialization.c:58-61 is
+ * OpenMP + FFTW threads). Spectral space is split into blocks of retained kx columns,
+ * physical space into blocks of y rows; the two global transposes of every 2-D transform
+ * are peer-memory stores fused into the producing kernels (no collective library on the
+ * data path). Available on the fast path only (grids 2048..16384 with Y1 == X2 == 1024).
+ *   nsb_mgpu_setup       partition for (rank, world); call before nsb_upload
+ *   nsb_mgpu_export      one process per device: 3 x 64-byte CUDA IPC handles (T, T', scalars)
+ *   nsb_mgpu_import      ... of peer `peer`, as gathered by the caller (torch.distributed, MPI, ...)
+ *   nsb_mgpu_link_local  one process driving all devices: enable peer access, swap pointers
+ *   nsb_mgpu_group_step  ns_spectral_advance_rk4 on such a group (nsb_rk4_step is used
+ *                        per rank in the one-process-per-device mode)
+ *   nsb_mgpu_partition   out = {rank, world, col0, col1, row0, rows}
+ * nsb_upload / nsb_download keep the reference layout; after steps only the own columns
+ * [col0, col1) of OMEGA_HAT are current on each device.
+ */
+int nsb_mgpu_setup(nsb_ctx *c, int rank, int world);
+int nsb_mgpu_partition(nsb_ctx *c, int out[6]);
+int nsb_mgpu_export(nsb_ctx *c, unsigned char *handles);
+int nsb_mgpu_import(nsb_ctx *c, int peer, const unsigned char *handles);
+int nsb_mgpu_link_local(nsb_ctx **ctxs, int n);
+int nsb_mgpu_group_step(nsb_ctx **ctxs, int n, double dt);
+
 /* number of kernels this library has launched on this context */
 long long nsb_launch_count(nsb_ctx *c);
 

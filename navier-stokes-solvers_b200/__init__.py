@@ -90,6 +90,12 @@ def load_nsb(path=None):
         "nsb_profile_end": [C.c_void_p, c_double_p, C.POINTER(C.c_int)],
         "nsb_timer_start": [C.c_void_p],
         "nsb_timer_stop": [C.c_void_p, C.POINTER(C.c_float)],
+        "nsb_mgpu_setup": [C.c_void_p, C.c_int, C.c_int],
+        "nsb_mgpu_partition": [C.c_void_p, C.POINTER(C.c_int)],
+        "nsb_mgpu_export": [C.c_void_p, C.c_char_p],
+        "nsb_mgpu_import": [C.c_void_p, C.c_int, C.c_char_p],
+        "nsb_mgpu_link_local": [C.POINTER(C.c_void_p), C.c_int],
+        "nsb_mgpu_group_step": [C.POINTER(C.c_void_p), C.c_int, C.c_double],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -247,8 +253,69 @@ class NsbContext:
         self._ck(self.lib.nsb_timer_stop(self.h, C.byref(ms)))
         return float(ms.value)
 
+    # ---- slab decomposition (include/nsb.h: nsb_mgpu_*) ----
+    def mgpu_setup(self, rank, world):
+        self._ck(self.lib.nsb_mgpu_setup(self.h, rank, world))
+
+    def partition(self):
+        out = (C.c_int * 6)()
+        self._ck(self.lib.nsb_mgpu_partition(self.h, out))
+        return dict(zip(["rank", "world", "col0", "col1", "row0", "rows"], out[:]))
+
+    def mgpu_export(self):
+        buf = C.create_string_buffer(192)
+        self._ck(self.lib.nsb_mgpu_export(self.h, buf))
+        return buf.raw
+
+    def mgpu_import(self, peer, handles):
+        self._ck(self.lib.nsb_mgpu_import(self.h, peer, handles))
+
     def launch_count(self):
         return int(self.lib.nsb_launch_count(self.h))
 
     def stream(self):
         return self.lib.nsb_stream(self.h)
+
+
+class NsbGroup:
+    """One process driving `world` devices: slab-decomposed contexts linked through peer memory
+    (nsb_mgpu_link_local / nsb_mgpu_group_step)."""
+
+    def __init__(self, nx, ny, world, devices=None, lib=None, **kw):
+        self.lib = lib if lib is not None else load_nsb()
+        devices = devices if devices is not None else list(range(world))
+        self.ctx = [NsbContext(nx, ny, device=devices[r], lib=self.lib, **kw) for r in range(world)]
+        for r, c in enumerate(self.ctx):
+            c.mgpu_setup(r, world)
+        self._arr = (C.c_void_p * world)(*[c.h for c in self.ctx])
+        if self.lib.nsb_mgpu_link_local(self._arr, world) != 0:
+            raise NsbError(self.lib.nsb_last_error().decode())
+        self.world = world
+
+    def each(self, fn):
+        return [fn(c) for c in self.ctx]
+
+    def upload(self, field, arr):
+        self.each(lambda c: c.upload(field, arr))
+
+    def step(self, dt=0.0):
+        if self.lib.nsb_mgpu_group_step(self._arr, self.world, float(dt)) != 0:
+            raise NsbError(self.lib.nsb_last_error().decode())
+
+    def sync(self):
+        self.each(lambda c: c.sync())
+
+    def download_omega_hat(self):
+        """Merge the own-column blocks of all devices (masked / unowned modes from rank 0)."""
+        out = None
+        for c in self.ctx:
+            a = c.download(OMEGA_HAT)
+            p = c.partition()
+            if out is None:
+                out = a
+            else:
+                out[:, p["col0"]:p["col1"]] = a[:, p["col0"]:p["col1"]]
+        return out
+
+    def close(self):
+        self.each(lambda c: c.close())

@@ -36,11 +36,14 @@
 #define NSB_CH_ROWS 16
 
 struct ChainArgs {
-    const cd *T; /* alpha output, 4 fields (stride fsT, pitch PT) */
-    cd *Tp;      /* F output = alpha_fwd input (pitch PT) */
+    const cd *T; /* alpha output, 4 fields x rowsT own rows (pitch PT) */
+    int rowsT;   /* y rows this device owns (ny when there is one device) */
+    int ybase;   /* first own row */
+    cd *Tpp[NSB_MAXP]; /* T' of every device, [ny][cb] own columns: F pushes each column to its owner */
+    int cb;      /* columns per device (the pitch of T') */
     cd *Z;       /* [slot][pp][q][1024] packed comb spectra */
     cd *P;       /* [slot][pair][1024] packed forward spectra */
-    int nslab;   /* ny / 16 */
+    int nslab;   /* own slabs: rowsT / 16 */
     int nslotZ, nslotP;
     int GY;      /* y1 values per slab = 16 / Y2 */
     int NQ;      /* combs per slab = 16 * X1 */
@@ -70,7 +73,7 @@ __device__ __forceinline__ void chain_B_step1(const NsbGeom &g, const ChainArgs 
         const int y1 = slab * a.GY + gy;
         cd x[Y2];
         if (col >= 0) {
-            const cd *in = a.T + (size_t)(fi ? fb : fa) * g.fsT + (size_t)(y1 * Y2) * g.PT + col;
+            const cd *in = a.T + ((size_t)(fi ? fb : fa) * a.rowsT + (size_t)(y1 * Y2)) * g.PT + col;
 #pragma unroll
             for (int j2 = 0; j2 < Y2; ++j2) x[j2] = nsb_ldcs(&in[(size_t)j2 * g.PT]);
             nsb_dft<Y2, true>(x);
@@ -315,9 +318,11 @@ __device__ __forceinline__ void chain_F_step2(const NsbGeom &g, const ChainArgs 
 #pragma unroll
         for (int y2 = 0; y2 < Y2; ++y2) x[y2] = tile[(size_t)((gy * Y2 + y2) * nseg + seg) * g.BC + cc];
         nsb_dft<Y2, false>(x);
-        cd *out = a.Tp + (size_t)((slab * a.GY + gy) * Y2) * g.PT + col;
+        /* the device that owns column `col` receives it (local store or NVLink peer store) */
+        const int owner = col / a.cb;
+        cd *out = a.Tpp[owner] + (size_t)(a.ybase + (slab * a.GY + gy) * Y2) * a.cb + (col - owner * a.cb);
 #pragma unroll
-        for (int j2 = 0; j2 < Y2; ++j2) nsb_stcs(&out[(size_t)j2 * g.PT], x[j2]);
+        for (int j2 = 0; j2 < Y2; ++j2) nsb_stcs(&out[(size_t)j2 * a.cb], x[j2]);
     }
 }
 
@@ -394,7 +399,7 @@ __device__ __forceinline__ void chain_B_issue(const NsbGeom &g, const ChainArgs 
         const int f = pp == 0 ? (fi ? 3 : 0) : (fi ? 2 : 1);
         const int col0 = (seg < a.nd) ? seg * g.X2 + kb : (seg - a.nd) * g.X2 + g.X2 - kb - (g.BC - 1);
         nsb_tma_2d_g2s(tile + (size_t)(fi * nseg + seg) * NSB_CH_ROWS * g.BC, tmT, 2 * col0,
-                       f * g.ny + slab * NSB_CH_ROWS, bar);
+                       f * a.rowsT + slab * NSB_CH_ROWS, bar);
     }
 }
 

@@ -78,6 +78,18 @@ struct nsb_ctx {
     int ch_slotZ, ch_slotP, ch_leadG, ch_leadF, ch_ctas, ch_btma;
     nsb_tmap tmT; /* tensor map of T in bufA (TMA-fed B) */
     int tmT_ok;
+    /* slab decomposition over the devices of one NVSwitch domain */
+    int mg_rank, mg_world;
+    int mg_cb, mg_c0, mg_c1;     /* columns per device, own column range */
+    int mg_rows, mg_row_shift;   /* own y rows = ny / world */
+    cd *bufTp;                   /* T' exchange buffer [ny][cb] (peers push into it) */
+    cd *mg_T[NSB_MAXP], *mg_Tp[NSB_MAXP];
+    NsbScalars *mg_sc[NSB_MAXP];
+    int mg_ipc;                  /* peers mapped through CUDA IPC (one process per device) */
+    unsigned mg_epoch;
+    void *mg_opened[3 * NSB_MAXP];
+    int mg_nopened;
+    cudaEvent_t mg_ev;
     int sm_count;
     long long launches;
     std::set<const void *> *smem_set;
@@ -248,6 +260,18 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     CK(cudaMalloc((void **)&c->bufB, c->buf_elems * sizeof(cd)));
     CK(cudaMemset(c->bufA, 0, c->buf_elems * sizeof(cd)));
     CK(cudaMemset(c->bufB, 0, c->buf_elems * sizeof(cd)));
+    c->bufTp = nullptr;
+    if (c->chain_mode) {
+        CK(cudaMalloc((void **)&c->bufTp, g.fsT * sizeof(cd)));
+        CK(cudaMemset(c->bufTp, 0, g.fsT * sizeof(cd)));
+    }
+    c->mg_rank = 0; c->mg_world = 1;
+    c->mg_cb = g.PT; c->mg_c0 = 0; c->mg_c1 = g.ncol;
+    c->mg_rows = g.ny; c->mg_row_shift = 30;
+    memset(c->mg_T, 0, sizeof(c->mg_T)); memset(c->mg_Tp, 0, sizeof(c->mg_Tp)); memset(c->mg_sc, 0, sizeof(c->mg_sc));
+    c->mg_T[0] = c->bufA; c->mg_Tp[0] = c->bufTp;
+    c->mg_ipc = 0; c->mg_epoch = 0; c->mg_nopened = 0;
+    CK(cudaEventCreateWithFlags(&c->mg_ev, cudaEventDisableTiming));
 
     /* wavenumber tables exactly as spectral_initialization.c:25-36 */
     std::vector<double> kx(g.nkx), ky(g.ny);
@@ -275,6 +299,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
 
     CK(cudaMalloc((void **)&c->d_sc, sizeof(NsbScalars)));
     CK(cudaMemset(c->d_sc, 0, sizeof(NsbScalars)));
+    c->mg_sc[0] = c->d_sc;
     CK(cudaMallocHost((void **)&c->h_sc, sizeof(NsbScalars)));
     memset(c->h_sc, 0, sizeof(NsbScalars));
     memset(&c->hv, 0, sizeof(c->hv));
@@ -307,6 +332,9 @@ extern "C" void nsb_ctx_destroy(nsb_ctx *c) {
     if (c->kWst) cudaFree(c->kWst);
     if (c->kACC) cudaFree(c->kACC);
     if (c->kSFD) cudaFree(c->kSFD);
+    for (int k = 0; k < c->mg_nopened; ++k) cudaIpcCloseMemHandle(c->mg_opened[k]);
+    if (c->bufTp) cudaFree(c->bufTp);
+    cudaEventDestroy(c->mg_ev);
     if (c->chZ) cudaFree(c->chZ);
     if (c->chP) cudaFree(c->chP);
     if (c->chCtr) cudaFree(c->chCtr);
@@ -390,13 +418,13 @@ static bool alpha_fast_ok(const nsb_ctx *c) { return c->fast && c->g.Y1 == 1024 
 
 static int klayout_copy(nsb_ctx *c, bool to_k, cd *ref, cd *K) {
     const NsbGeom &g = c->g;
-    const dim3 grid((g.ncol + 31) / 32, g.Y1 / 32, g.Y2), block(32, 8);
+    const dim3 grid((c->mg_c1 - c->mg_c0 + 31) / 32, g.Y1 / 32, g.Y2), block(32, 8);
     if (to_k) {
         auto k = k_ref_to_klayout;
-        NSB_LAUNCH(k, grid, block, 0, c->stream, g, (const cd *)ref, K);
+        NSB_LAUNCH(k, grid, block, 0, c->stream, g, (const cd *)ref, K, c->mg_c0, c->mg_c1);
     } else {
         auto k = k_klayout_to_ref;
-        NSB_LAUNCH(k, grid, block, 0, c->stream, g, (const cd *)K, ref);
+        NSB_LAUNCH(k, grid, block, 0, c->stream, g, (const cd *)K, ref, c->mg_c0, c->mg_c1);
     }
     CKL();
     c->launches++;
@@ -420,7 +448,7 @@ static int sync_ref(nsb_ctx *c) {
 
 /* make the K-layout state current (before fast-path steps) */
 static int sync_k(nsb_ctx *c) {
-    const size_t bytes = (size_t)c->g.ncol * c->g.ny * sizeof(cd);
+    const size_t bytes = (size_t)(c->mg_c1 - c->mg_c0) * c->g.ny * sizeof(cd);
     if (!c->kW0) {
         CK(cudaMalloc((void **)&c->kW0, bytes));
         CK(cudaMalloc((void **)&c->kWst, bytes));
@@ -660,9 +688,22 @@ static int launch_beta(nsb_ctx *c, bool inverse, const BetaArgs &a) {
     return fail("unsupported Y2=%d", c->g.Y2);
 }
 
+/* T / T' locations and the slab partition of the fused column kernel */
+static void fill_alpha_fast(nsb_ctx *c, AlphaFastArgs &fa, const cd *tp, int tp_pitch) {
+    const NsbGeom &g = c->g;
+    fa.in = tp;
+    fa.in_pitch = tp_pitch;
+    for (int p = 0; p < NSB_MAXP; ++p) fa.outp[p] = c->mg_T[p < c->mg_world ? p : 0];
+    fa.out_fs = (size_t)c->mg_rows * g.PT;
+    fa.out_pitch = g.PT;
+    fa.row_shift = c->mg_row_shift;
+    fa.c0 = c->mg_c0;
+    fa.c1 = c->mg_c1;
+}
+
 static int launch_alpha1024(nsb_ctx *c, bool fwd, bool inv, const AlphaFastArgs &a) {
     const NsbGeom &g = c->g;
-    const dim3 grid((g.ncol + NSB_A1024_COLS - 1) / NSB_A1024_COLS, g.Y2), block(128);
+    const dim3 grid((a.c1 - a.c0 + NSB_A1024_COLS - 1) / NSB_A1024_COLS, g.Y2), block(128);
     const size_t smem = NSB_A1024_SMEM;
     prof_pre(c, fwd ? PK_ALPHA_FWD : PK_ALPHA_INV);
     if (fwd && inv) {
@@ -763,14 +804,17 @@ static int make_tmap_2d(nsb_tmap *out, const void *base, size_t dim0, size_t dim
 #endif
 }
 
-/* T (bufA, 4 fields) -> T' (bufB): B, G, F of nsb_chain.cuh */
+/* T (bufA, 4 fields, own rows) -> T' (bufTp of the column owners): B, G, F of nsb_chain.cuh */
 static int launch_chain(nsb_ctx *c, bool want_umax) {
     const NsbGeom &g = c->g;
     ChainArgs a;
     memset(&a, 0, sizeof(a));
     a.T = c->bufA;
-    a.Tp = c->bufB;
-    a.nslab = g.ny / NSB_CH_ROWS;
+    a.rowsT = c->mg_rows;
+    a.ybase = c->mg_rank * c->mg_rows;
+    for (int p = 0; p < NSB_MAXP; ++p) a.Tpp[p] = c->mg_Tp[p < c->mg_world ? p : 0];
+    a.cb = c->mg_cb;
+    a.nslab = c->mg_rows / NSB_CH_ROWS;
     a.GY = NSB_CH_ROWS / g.Y2;
     a.NQ = NSB_CH_ROWS * g.X1;
     a.nbatch = (g.X2h + 1 + g.BC - 1) / g.BC; /* every k2 of a comb spectrum is written, also when X1 == 1 */
@@ -783,7 +827,7 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
     const size_t tileF = tileB / 2 + twtab;
     const size_t smemG = NSB_CH_TW_BYTES + (size_t)W * (want_umax ? NSB_CHG_WARP_BYTES(1) : NSB_CHG_WARP_BYTES(0));
     if (c->chain_mode == 1) {
-        /* Z in bufB, P in bufA (T is dead once B has run), T' back in bufB (Z dead after G) */
+        /* Z in bufB, P in bufA (T is dead once B has run), T' into the owners' exchange buffers */
         a.nslotZ = a.nslotP = a.nslab;
         a.Z = c->bufB;
         a.P = c->bufA;
@@ -793,7 +837,7 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
             const size_t smemB = 2 * tileB + 64 + 128 + twtab;
             if (ensure_smem(c, k, smemB, true)) return -1;
             if (!c->tmT_ok) {
-                if (make_tmap_2d(&c->tmT, c->bufA, (size_t)2 * g.PT, (size_t)4 * g.ny, (size_t)g.PT * sizeof(cd),
+                if (make_tmap_2d(&c->tmT, c->bufA, (size_t)2 * g.PT, (size_t)4 * c->mg_rows, (size_t)g.PT * sizeof(cd),
                                  2 * g.BC, NSB_CH_ROWS))
                     return -1;
                 c->tmT_ok = 1;
@@ -1081,8 +1125,18 @@ extern "C" int nsb_hyperviscosity_post_step(nsb_ctx *c, int state_hat, double dt
 
 static int launch_cfl(nsb_ctx *c) {
     const double dx_min = fmin(c->prm.Lx / c->g.nx, c->prm.Ly / c->g.ny);
-    auto k = k_cfl_dt;
-    NSB_LAUNCH(k, dim3(1), dim3(32), 0, c->stream, c->d_sc, c->prm.cfl_factor, dx_min, c->prm.Re, NSB_MIN_DT, NSB_MAX_DT);
+    if (c->mg_world > 1) {
+        /* max |u|^2 over the slabs of all devices, read from their scalar blocks (peer memory) */
+        NsbPeerScalars ps;
+        for (int p = 0; p < NSB_MAXP; ++p) ps.sc[p] = c->mg_sc[p < c->mg_world ? p : 0];
+        auto k = k_cfl_dt_multi;
+        NSB_LAUNCH(k, dim3(1), dim3(32), 0, c->stream, c->d_sc, ps, c->mg_world, c->prm.cfl_factor, dx_min, c->prm.Re,
+                   NSB_MIN_DT, NSB_MAX_DT);
+    } else {
+        auto k = k_cfl_dt;
+        NSB_LAUNCH(k, dim3(1), dim3(32), 0, c->stream, c->d_sc, c->prm.cfl_factor, dx_min, c->prm.Re, NSB_MIN_DT,
+                   NSB_MAX_DT);
+    }
     CKL();
     c->launches++;
     return 0;
@@ -1127,9 +1181,95 @@ extern "C" int nsb_cfl_timestep(nsb_ctx *c, double *dt_out) {
     return 0;
 }
 
+/*
+ * The slab-decomposed fast path (Y1 == X2 == 1024, chain kernels) as a sequence of phases
+ * with a device barrier between them:
+ *   0           K-layout state current, dt, alpha_inv of stage 1     -> T pushed to row owners
+ *   1,3,5,7     chain B/G/F of stage 1..4                            -> T' pushed to column owners
+ *   2,4,6       (stage 1: CFL dt from the max over all slabs) alpha fwd + RK + inv of the next stage
+ *   8           alpha fwd + RK final combine, t += dt
+ */
+#define NSB_FAST_PHASES 9
+
+static void fill_rk(nsb_ctx *c, NsbRk &rk, int stage) {
+    memset(&rk, 0, sizeof(rk));
+    rk.stage = stage;
+    rk.W0 = c->kW0; rk.Wst = c->kWst; rk.ACC = c->kACC; rk.SFD = c->kSFD;
+    rk.dt = &c->d_sc->dt;
+    rk.inv_Re = 1.0 / c->prm.Re;
+    rk.hv = c->hv;
+    rk.FB = c->force_on ? c->d_force : nullptr;
+    rk.ib = c->ib; rk.jb = c->jb;
+}
+
+static int fast_phase(nsb_ctx *c, int ph, double dt) {
+    const bool device_dt = !(dt > 0.0);
+    CK(cudaSetDevice(c->device));
+    if (ph == 0) {
+        if (sync_k(c)) return -1;
+        if (c->mg_world > 1) /* peers read it during the previous step's CFL, long before this point */
+            CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
+        if (!device_dt) {
+            auto k = k_set_dt;
+            NSB_LAUNCH(k, dim3(1), dim3(32), 0, c->stream, c->d_sc, dt);
+            CKL();
+            c->launches++;
+        }
+        AlphaFastArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fill_alpha_fast(c, fa, nullptr, 0);
+        fa.Wsrc = c->kW0;
+        fill_rk(c, fa.rk, 1);
+        return launch_alpha1024(c, false, true, fa);
+    }
+    if (ph & 1) { /* chain of stage (ph + 1) / 2 */
+        return launch_chain(c, device_dt && ph == 1);
+    }
+    const int stage = ph / 2;
+    if (stage == 1 && device_dt && launch_cfl(c)) return -1;
+    AlphaFastArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fill_alpha_fast(c, fa, c->bufTp, c->mg_cb);
+    fill_rk(c, fa.rk, stage);
+    if (launch_alpha1024(c, true, stage < 4, fa)) return -1;
+    if (stage == 4) {
+        auto k = k_step_end;
+        NSB_LAUNCH(k, dim3(1), dim3(32), 0, c->stream, c->d_sc);
+        CKL();
+        c->launches++;
+    }
+    return 0;
+}
+
+/* one process per device: every device announces `epoch` in the scalar block of every peer
+ * and waits until all peers have announced it to this device (stream ordered, no host) */
+static int peer_barrier_ipc(nsb_ctx *c) {
+    NsbPeerScalars ps;
+    for (int p = 0; p < NSB_MAXP; ++p) ps.sc[p] = c->mg_sc[p < c->mg_world ? p : 0];
+    c->mg_epoch += 1;
+    auto k = k_peer_barrier;
+    NSB_LAUNCH(k, dim3(1), dim3(32), 0, c->stream, c->d_sc, ps, c->mg_rank, c->mg_world, c->mg_epoch);
+    CKL();
+    c->launches++;
+    return 0;
+}
+
+static bool fast_chain_ok(const nsb_ctx *c) { return alpha_fast_ok(c) && c->chain_mode == 1; }
+
 extern "C" int nsb_rk4_step(nsb_ctx *c, double dt) {
     if (!c) return fail("null context");
     CK(cudaSetDevice(c->device));
+    if (fast_chain_ok(c)) {
+        if (c->mg_world > 1 && !c->mg_ipc)
+            return fail("this context is part of a single-process device group: use nsb_mgpu_group_step");
+        for (int ph = 0; ph < NSB_FAST_PHASES; ++ph) {
+            if (fast_phase(c, ph, dt)) return -1;
+            if (c->mg_world > 1 && ph + 1 < NSB_FAST_PHASES && peer_barrier_ipc(c)) return -1;
+        }
+        return 0;
+    }
+    if (c->mg_world > 1)
+        return fail("slab decomposition needs the fast path (Y1 == X2 == 1024, masked modes zero, NSB_CHAIN=1)");
     void *w0, *wst, *acc, *sfd = nullptr;
     if (get_field(c, NSB_OMEGA_HAT, &w0) || get_field(c, NSB_OMEGA_STAGE, &wst) || get_field(c, NSB_RK_ACC, &acc))
         return -1;
@@ -1167,7 +1307,8 @@ extern "C" int nsb_rk4_step(nsb_ctx *c, double dt) {
             if (stage == 1) {
                 AlphaFastArgs fa;
                 memset(&fa, 0, sizeof(fa));
-                fa.out = c->bufA; fa.out_fs = g.fsT; fa.out_pitch = g.PT; fa.Wsrc = c->kW0; fa.rk = rk;
+                fill_alpha_fast(c, fa, nullptr, 0);
+                fa.Wsrc = c->kW0; fa.rk = rk;
                 if (launch_alpha1024(c, false, true, fa)) return -1;
             }
         } else {
@@ -1184,12 +1325,12 @@ extern "C" int nsb_rk4_step(nsb_ctx *c, double dt) {
             if (afast) {
                 AlphaFastArgs fa;
                 memset(&fa, 0, sizeof(fa));
-                fa.in = c->bufB; fa.in_pitch = g.PT;
-                fa.out = c->bufA; fa.out_fs = g.fsT; fa.out_pitch = g.PT; fa.rk = rk;
+                fill_alpha_fast(c, fa, c->bufTp, c->mg_cb);
+                fa.rk = rk;
                 if (launch_alpha1024(c, true, stage < 4, fa)) return -1;
             } else {
-                af.in = c->bufB;
-                af.in_pitch = g.PT;
+                af.in = c->bufTp;
+                af.in_pitch = c->mg_cb;
                 if (launch_alpha_fwd(c, NSB_EPI_RK, af)) return -1;
                 if (c->masked_nonzero) {
                     auto k = k_rk_masked;
@@ -1226,8 +1367,8 @@ extern "C" int nsb_rk4_step(nsb_ctx *c, double dt) {
             }
             AlphaFastArgs fa;
             memset(&fa, 0, sizeof(fa));
-            fa.in = Tp; fa.in_pitch = g.PT;
-            fa.out = c->bufA; fa.out_fs = g.fsT; fa.out_pitch = g.PT; fa.rk = rk;
+            fill_alpha_fast(c, fa, Tp, g.PT);
+            fa.rk = rk;
             if (launch_alpha1024(c, true, stage < 4, fa)) return -1;
             continue;
         }
@@ -1339,5 +1480,149 @@ extern "C" int nsb_get_plan(nsb_ctx *c, int out[8]) {
     out[0] = g.Y1; out[1] = g.Y2; out[2] = g.X1; out[3] = g.X2;
     out[4] = g.C; out[5] = g.BC; out[6] = g.ncol;
     out[7] = 4 * (c->has_beta ? 5 : 3) + 2;
+    return 0;
+}
+
+/* ------------------------------------------------------------- slab decomposition */
+
+extern "C" int nsb_mgpu_setup(nsb_ctx *c, int rank, int world) {
+    if (!c) return fail("null context");
+    if (world < 1 || world > NSB_MAXP || rank < 0 || rank >= world) return fail("bad rank %d / world %d", rank, world);
+    if ((world & (world - 1)) != 0) return fail("world size must be a power of two (got %d)", world);
+    CK(cudaSetDevice(c->device));
+    const NsbGeom &g = c->g;
+    if (world > 1) {
+        if (!(c->fast && g.Y1 == 1024 && c->chain_mode == 1))
+            return fail("slab decomposition needs Y1 == X2 == 1024 with a beta split (grids 2048..16384) and NSB_CHAIN=1");
+        if ((g.ny / world) % NSB_CH_ROWS != 0) return fail("ny / world must be a multiple of %d", NSB_CH_ROWS);
+    }
+    if (sync_ref(c)) return -1;
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->kW0) { cudaFree(c->kW0); cudaFree(c->kWst); cudaFree(c->kACC); c->kW0 = c->kWst = c->kACC = nullptr; }
+    if (c->kSFD) { cudaFree(c->kSFD); c->kSFD = nullptr; }
+    c->k_truth = 0;
+    c->mg_rank = rank;
+    c->mg_world = world;
+    if (world == 1) {
+        c->mg_cb = g.PT; c->mg_c0 = 0; c->mg_c1 = g.ncol; c->mg_rows = g.ny; c->mg_row_shift = 30;
+    } else {
+        c->mg_cb = ((g.ncol + world - 1) / world + NSB_A1024_COLS - 1) / NSB_A1024_COLS * NSB_A1024_COLS;
+        c->mg_c0 = rank * c->mg_cb;
+        c->mg_c1 = c->mg_c0 + c->mg_cb < g.ncol ? c->mg_c0 + c->mg_cb : g.ncol;
+        if (c->mg_c1 < c->mg_c0) c->mg_c1 = c->mg_c0;
+        c->mg_rows = g.ny / world;
+        int sh = 0;
+        while ((1 << sh) < c->mg_rows) ++sh;
+        c->mg_row_shift = sh;
+    }
+    for (int p = 0; p < NSB_MAXP; ++p) { c->mg_T[p] = nullptr; c->mg_Tp[p] = nullptr; c->mg_sc[p] = nullptr; }
+    c->mg_T[rank] = c->bufA; c->mg_Tp[rank] = c->bufTp; c->mg_sc[rank] = c->d_sc;
+    if (world == 1) { c->mg_T[0] = c->bufA; c->mg_Tp[0] = c->bufTp; c->mg_sc[0] = c->d_sc; }
+    c->tmT_ok = 0;
+    c->mg_ipc = 0;
+    c->mg_epoch = 0;
+    CK(cudaMemset(c->d_sc->peer_flags, 0, sizeof(c->d_sc->peer_flags)));
+    return 0;
+}
+
+extern "C" int nsb_mgpu_partition(nsb_ctx *c, int out[6]) {
+    if (!c || !out) return fail("nsb_mgpu_partition: null argument");
+    out[0] = c->mg_rank; out[1] = c->mg_world; out[2] = c->mg_c0; out[3] = c->mg_c1;
+    out[4] = c->mg_rank * c->mg_rows; out[5] = c->mg_rows;
+    return 0;
+}
+
+/* CUDA IPC handles of the three buffers peers write to / read from: T, T', scalars */
+extern "C" int nsb_mgpu_export(nsb_ctx *c, unsigned char *handles /* 3 x 64 bytes */) {
+    if (!c || !handles) return fail("nsb_mgpu_export: null argument");
+#ifdef NSB_EMULATE
+    return fail("CUDA IPC is not available under the emulator");
+#else
+    CK(cudaSetDevice(c->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *ptrs[3] = {c->bufA, c->bufTp, c->d_sc};
+    for (int k = 0; k < 3; ++k) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ptrs[k]));
+        memcpy(handles + 64 * k, &h, 64);
+    }
+    return 0;
+#endif
+}
+
+extern "C" int nsb_mgpu_import(nsb_ctx *c, int peer, const unsigned char *handles) {
+    if (!c || !handles) return fail("nsb_mgpu_import: null argument");
+    if (peer < 0 || peer >= c->mg_world) return fail("bad peer %d", peer);
+    if (peer == c->mg_rank) return 0;
+#ifdef NSB_EMULATE
+    return fail("CUDA IPC is not available under the emulator");
+#else
+    CK(cudaSetDevice(c->device));
+    void *ptrs[3];
+    for (int k = 0; k < 3; ++k) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * k, 64);
+        CK(cudaIpcOpenMemHandle(&ptrs[k], h, cudaIpcMemLazyEnablePeerAccess));
+        c->mg_opened[c->mg_nopened++] = ptrs[k];
+    }
+    c->mg_T[peer] = (cd *)ptrs[0];
+    c->mg_Tp[peer] = (cd *)ptrs[1];
+    c->mg_sc[peer] = (NsbScalars *)ptrs[2];
+    c->mg_ipc = 1;
+    return 0;
+#endif
+}
+
+/* single process driving n devices: enable peer access and exchange raw pointers */
+extern "C" int nsb_mgpu_link_local(nsb_ctx **cs, int n) {
+    if (!cs || n < 1 || n > NSB_MAXP) return fail("nsb_mgpu_link_local: bad arguments");
+    for (int i = 0; i < n; ++i) {
+        if (!cs[i] || cs[i]->mg_world != n || cs[i]->mg_rank != i)
+            return fail("nsb_mgpu_link_local: context %d is not set up as rank %d of %d", i, i, n);
+    }
+    for (int i = 0; i < n; ++i) {
+        CK(cudaSetDevice(cs[i]->device));
+        for (int j = 0; j < n; ++j) {
+            if (i != j && cs[i]->device != cs[j]->device) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(cs[j]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail("cudaDeviceEnablePeerAccess(%d -> %d): %s", cs[i]->device, cs[j]->device,
+                                cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            cs[i]->mg_T[j] = cs[j]->bufA;
+            cs[i]->mg_Tp[j] = cs[j]->bufTp;
+            cs[i]->mg_sc[j] = cs[j]->d_sc;
+        }
+        cs[i]->mg_ipc = 0;
+    }
+    return 0;
+}
+
+/* all streams of the group wait for everything recorded so far on all of them */
+static int group_barrier(nsb_ctx **cs, int n) {
+    for (int i = 0; i < n; ++i) {
+        CK(cudaSetDevice(cs[i]->device));
+        CK(cudaEventRecord(cs[i]->mg_ev, cs[i]->stream));
+    }
+    for (int j = 0; j < n; ++j) {
+        CK(cudaSetDevice(cs[j]->device));
+        for (int i = 0; i < n; ++i)
+            if (i != j) CK(cudaStreamWaitEvent(cs[j]->stream, cs[i]->mg_ev, 0));
+    }
+    return 0;
+}
+
+/* ns_spectral_advance_rk4 on a single-process device group (asynchronous) */
+extern "C" int nsb_mgpu_group_step(nsb_ctx **cs, int n, double dt) {
+    if (!cs || n < 1 || n > NSB_MAXP) return fail("nsb_mgpu_group_step: bad arguments");
+    for (int i = 0; i < n; ++i)
+        if (!cs[i] || !fast_chain_ok(cs[i]) || cs[i]->mg_world != n)
+            return fail("nsb_mgpu_group_step: context %d is not on the slab-decomposed fast path", i);
+    for (int ph = 0; ph < NSB_FAST_PHASES; ++ph) {
+        for (int i = 0; i < n; ++i)
+            if (fast_phase(cs[i], ph, dt)) return -1;
+        if (n > 1 && ph + 1 < NSB_FAST_PHASES && group_barrier(cs, n)) return -1;
+    }
     return 0;
 }

@@ -704,6 +704,7 @@ struct NsbScalars {
     unsigned masked_nonzero;
     int step;
     double dt_hist[256];
+    unsigned peer_flags[8];        /* device barrier of the slab decomposition: epoch announced by each peer */
 };
 
 /* spectral_time_integration.c:22-30 : dt = clamp(min(cfl*dx/(|u|max+1e-12), 0.5*Re*dx^2)) */
@@ -717,6 +718,43 @@ __global__ void k_cfl_dt(NsbScalars *sc, double cfl, double dx_min, double Re, d
     dt = fmin(dt, max_dt);
     sc->dt = dt;
     sc->umax_bits = 0ull;
+}
+
+struct NsbPeerScalars {
+    NsbScalars *sc[8];
+};
+
+/* the same, with max |u| taken over the slabs of all devices (their scalar blocks are peer memory) */
+__global__ void k_cfl_dt_multi(NsbScalars *sc, NsbPeerScalars ps, int world, double cfl, double dx_min, double Re,
+                               double min_dt, double max_dt) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long bits = 0ull;
+    for (int p = 0; p < world; ++p) {
+        const unsigned long long b = *reinterpret_cast<volatile unsigned long long *>(&ps.sc[p]->umax_bits);
+        if (b > bits) bits = b;
+    }
+    const double max_vel = __dsqrt_rn(__longlong_as_double((long long)bits));
+    const double dt_cfl = __ddiv_rn(__dmul_rn(cfl, dx_min), __dadd_rn(max_vel, 1e-12));
+    const double dt_visc = __dmul_rn(__dmul_rn(__dmul_rn(0.5, Re), dx_min), dx_min);
+    double dt = fmin(dt_cfl, dt_visc);
+    dt = fmax(dt, min_dt);
+    dt = fmin(dt, max_dt);
+    sc->dt = dt;
+}
+
+/*
+ * Device barrier across the processes of a slab-decomposed run: lane p announces `epoch`
+ * in peer p's scalar block (NVLink peer store after a system-scope fence, so the T / T'
+ * pushes of the preceding kernels are visible first) and then waits for peer p's
+ * announcement in the local block.
+ */
+__global__ void k_peer_barrier(NsbScalars *sc, NsbPeerScalars ps, int rank, int world, unsigned epoch) {
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    nsb_fence_system();
+    *reinterpret_cast<volatile unsigned *>(&ps.sc[p]->peer_flags[rank]) = epoch;
+    while (*reinterpret_cast<volatile unsigned *>(&sc->peer_flags[p]) < epoch) nsb_backoff();
+    nsb_fence_system();
 }
 
 __global__ void k_set_dt(NsbScalars *sc, double dt) {
@@ -869,41 +907,55 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gamma1024(NsbGeom g, GammaFas
  * owns column ic touch 512 contiguous bytes. Converted from / to the reference layout
  * (f_hat[j*nkx + i]) only at the API boundary (upload, download, diagnostics).
  */
-__global__ void __launch_bounds__(256) k_ref_to_klayout(NsbGeom g, const cd *ref, cd *K) {
+/* columns [c0, c1) are the ones this device owns (slab decomposition); K is indexed by ic - c0 */
+__global__ void __launch_bounds__(256) k_ref_to_klayout(NsbGeom g, const cd *ref, cd *K, int c0, int c1) {
     __shared__ cd tile[32][33];
-    /* grid: (ceil(ncol/32), Y1/32, Y2); block (32, 8) */
-    const int j2 = blockIdx.z, ic0 = blockIdx.x * 32, j10 = blockIdx.y * 32;
+    /* grid: (ceil((c1-c0)/32), Y1/32, Y2); block (32, 8) */
+    const int j2 = blockIdx.z, ic0 = c0 + blockIdx.x * 32, j10 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int j = (j10 + r) * g.Y2 + j2, ic = ic0 + threadIdx.x;
-        tile[r][threadIdx.x] = (ic < g.ncol) ? ref[(size_t)j * g.nkx + ic] : cmk(0.0, 0.0);
+        tile[r][threadIdx.x] = (ic < c1) ? ref[(size_t)j * g.nkx + ic] : cmk(0.0, 0.0);
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int ic = ic0 + r;
-        if (ic < g.ncol) K[((size_t)ic * g.Y2 + j2) * g.Y1 + j10 + threadIdx.x] = tile[threadIdx.x][r];
+        if (ic < c1) K[((size_t)(ic - c0) * g.Y2 + j2) * g.Y1 + j10 + threadIdx.x] = tile[threadIdx.x][r];
     }
 }
 
-__global__ void __launch_bounds__(256) k_klayout_to_ref(NsbGeom g, const cd *K, cd *ref) {
+__global__ void __launch_bounds__(256) k_klayout_to_ref(NsbGeom g, const cd *K, cd *ref, int c0, int c1) {
     __shared__ cd tile[32][33];
-    const int j2 = blockIdx.z, ic0 = blockIdx.x * 32, j10 = blockIdx.y * 32;
+    const int j2 = blockIdx.z, ic0 = c0 + blockIdx.x * 32, j10 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int ic = ic0 + r;
-        tile[r][threadIdx.x] = (ic < g.ncol) ? K[((size_t)ic * g.Y2 + j2) * g.Y1 + j10 + threadIdx.x] : cmk(0.0, 0.0);
+        tile[r][threadIdx.x] =
+            (ic < c1) ? K[((size_t)(ic - c0) * g.Y2 + j2) * g.Y1 + j10 + threadIdx.x] : cmk(0.0, 0.0);
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int j = (j10 + r) * g.Y2 + j2, ic = ic0 + threadIdx.x;
-        if (ic < g.ncol) ref[(size_t)j * g.nkx + ic] = tile[threadIdx.x][r];
+        if (ic < c1) ref[(size_t)j * g.nkx + ic] = tile[threadIdx.x][r];
     }
 }
 
+#define NSB_MAXP 8 /* devices of one NVSwitch domain */
+
+/*
+ * Slab decomposition: this device owns retained columns [c0, c1) in spectral
+ * space (K-layout state and T' are indexed by ic - c0) and the y rows
+ * [rank*2^row_shift, (rank+1)*2^row_shift) in physical space. The inverse output tile is
+ * PUSHED row by row into the T buffer of the device that owns the row (outp[owner], peer
+ * memory over NVLink; outp[0] is the local buffer when there is one device), i.e. the
+ * global transpose of the 2-D FFT is fused into the store phase of the column kernel.
+ */
 struct AlphaFastArgs {
-    const cd *in;    /* T' (forward input) */
+    const cd *in;    /* T' (forward input), [ny][in_pitch], local columns */
     int in_pitch;
-    cd *out;         /* T, 4 fields (inverse output) */
-    size_t out_fs;
+    cd *outp[NSB_MAXP]; /* T of every device: 4 fields x own rows x out_pitch */
+    size_t out_fs;   /* field stride of T (own rows * out_pitch) */
     int out_pitch;
+    int row_shift;   /* log2(rows per device) */
+    int c0, c1;      /* own columns */
     const cd *Wsrc;  /* K-layout state feeding the inverse part when there is no forward part */
     NsbRk rk;        /* K-layout pointers */
 };
@@ -965,9 +1017,9 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
     cd *S = smem + 1024;
     cd *TB = S + 1024 * NSB_A1024_COLS; /* TB[m] = exp(-2 pi i (32 j2 m)/ny) */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j2 = blockIdx.y, ic0 = blockIdx.x * NSB_A1024_COLS;
+    const int j2 = blockIdx.y, ic0 = a.c0 + blockIdx.x * NSB_A1024_COLS;
     const int ic = ic0 + warp;
-    const bool active = ic < g.ncol;
+    const bool active = ic < a.c1;
     const int cc = threadIdx.x & 3, rr = threadIdx.x >> 2; /* cooperative copies: 4 threads per row */
     nsb_fill_tw1024(TW, g.WY, g.ny / 1024);
     if (threadIdx.x < 32) TB[threadIdx.x] = __ldg(&g.WY[(size_t)32 * j2 * threadIdx.x]);
@@ -976,15 +1028,15 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
     double *KY = reinterpret_cast<double *>(TB + 32); /* ky of this CTA's rows, indexed by j1 */
     for (int k = threadIdx.x; k < 1024; k += blockDim.x) KY[k] = __ldg(&g.kyK[(size_t)j2 * 1024 + k]);
     const double kxv = active ? __ldg(&g.kx[ic]) : 0.0;
-    const size_t kbase = ((size_t)ic * g.Y2 + j2) * 1024;
+    const size_t kbase = ((size_t)(ic - a.c0) * g.Y2 + j2) * 1024;
     const cd *Wre = FWD ? a.rk.Wst : a.Wsrc; /* state the inverse fields derive from */
     if (FWD) {
-        const bool colok = ic0 + cc < g.ncol;
+        const bool colok = ic0 + cc < a.c1;
 #pragma unroll 8
         for (int i = 0; i < 32; ++i) {
             const int row = rr + 32 * i;
             cd v = cmk(0.0, 0.0);
-            if (colok) v = a.in[(size_t)(row * g.Y2 + j2) * a.in_pitch + ic0 + cc];
+            if (colok) v = a.in[(size_t)(row * g.Y2 + j2) * a.in_pitch + (ic0 - a.c0) + cc];
             S[nsb_sidx(row, cc)] = v;
         }
     }
@@ -1062,8 +1114,8 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
                     const int flat = threadIdx.x + 128 * (i0 + u);
                     const int c = flat >> 10, j1 = flat & 1023;
                     int icc = ic0 + c;
-                    if (icc >= g.ncol) icc = g.ncol - 1; /* clamped: loaded, never stored */
-                    kid[u] = ((size_t)icc * g.Y2 + j2) * 1024 + j1;
+                    if (icc >= a.c1) icc = a.c1 - 1; /* clamped: loaded, never stored */
+                    kid[u] = ((size_t)(icc - a.c0) * g.Y2 + j2) * 1024 + j1;
                     W0v[u] = a.rk.W0[kid[u]];
                     Wsv[u] = (a.rk.stage == 1) ? W0v[u] : a.rk.Wst[kid[u]];
                     ACv[u] = (a.rk.stage == 1) ? cmk(0.0, 0.0) : a.rk.ACC[kid[u]];
@@ -1075,7 +1127,7 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
                     const int c = flat >> 10, j1 = flat & 1023;
                     const int icc = ic0 + c;
                     const int band = nsb_band(j1 * g.Y2 + j2, g.ny);
-                    if (icc < g.ncol && nsb_iabs(band) <= g.ycut) {
+                    if (icc < a.c1 && nsb_iabs(band) <= g.ycut) {
                         const cd v = S[nsb_sidx(j1, c)];
                         const cd Nh = cmk(-(v.x * g.norm), -(v.y * g.norm));
                         cd acc, sfd;
@@ -1092,12 +1144,15 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
                 }
             }
         } else {
-            cd *out = a.out + (size_t)(job - 1) * a.out_fs;
-            if (ic0 + cc < g.ncol) {
+            if (ic0 + cc < a.c1) {
+                const size_t fo = (size_t)(job - 1) * a.out_fs + ic0 + cc;
+                const int rmask = (1 << a.row_shift) - 1;
 #pragma unroll 8
                 for (int i = 0; i < 32; ++i) {
                     const int row = rr + 32 * i;
-                    out[(size_t)(row * g.Y2 + j2) * a.out_pitch + ic0 + cc] = S[nsb_sidx(row, cc)];
+                    const int y = row * g.Y2 + j2;
+                    /* the device that owns row y receives it (local store or NVLink peer store) */
+                    a.outp[y >> a.row_shift][fo + (size_t)(y & rmask) * a.out_pitch] = S[nsb_sidx(row, cc)];
                 }
             }
         }

@@ -35,6 +35,7 @@ static inline void nsb_prefetch_l2(const void *) {}
 static inline unsigned nsb_ld_acquire(const unsigned *p) { return *p; }
 static inline void nsb_red_release(unsigned *p, unsigned v) { *p += v; }
 static inline void nsb_backoff() { nsbemu::yield(); }
+static inline void nsb_fence_system() {}
 #else
 __device__ __forceinline__ cd nsb_ldcg(const cd *p) { return __ldcg(p); }
 /* read-once / write-once streams (evict-first) so they do not displace the L2-resident rings */
@@ -51,6 +52,7 @@ __device__ __forceinline__ void nsb_red_release(unsigned *p, unsigned v) {
     atomicAdd(p, v);
 }
 __device__ __forceinline__ void nsb_backoff() { __nanosleep(64); }
+__device__ __forceinline__ void nsb_fence_system() { __threadfence_system(); }
 #endif
 
 /* correctly rounded FP64 reciprocal (MUFU.RCP64H + Newton, inlined: no division subroutine) */

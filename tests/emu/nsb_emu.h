@@ -139,6 +139,9 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0;
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
+enum { cudaErrorPeerAccessAlreadyEnabled = 704 };
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return 0; }
+static inline cudaError_t cudaIpcCloseMemHandle(void *) { return 0; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 
 #define NSB_LAUNCH(kernel, grid, block, smem, stream, ...) \

@@ -65,6 +65,8 @@ NSB_SYMBOLS = [
     "nsb_rk4_step", "nsb_diagnostics", "nsb_diagnostics_phys", "nsb_get_state", "nsb_set_time",
     "nsb_get_dt_history", "nsb_get_plan", "nsb_stream", "nsb_timer_start", "nsb_timer_stop", "nsb_profile_begin", "nsb_profile_end",
     "nsb_launch_count",
+    "nsb_mgpu_setup", "nsb_mgpu_partition", "nsb_mgpu_export", "nsb_mgpu_import", "nsb_mgpu_link_local",
+    "nsb_mgpu_group_step",
 ]
 
 

@@ -120,3 +120,36 @@ def test_emu_chain_matches_plain_kernels(nsb, emu_lib, monkeypatch):
     assert np.array_equal(out[1][0], out[2][0]) and out[1][1] == out[2][1]
     assert pc.rel(out[1][0], out[0][0]) < 1e-14
     assert abs(out[1][1] - out[0][1]) <= 1e-15 * out[0][1]
+
+
+def test_emu_slab_decomposition_two_devices(nsb, emu_lib):
+    """Two slab-decomposed contexts (kx-column blocks / y-row blocks, transposes as pushes into
+    the owner's buffers) against one context: the arithmetic per mode is the same, so
+    omega_hat and the device-side CFL dt must be bit-identical."""
+    import numpy as np
+    nx, ny = 1024, 2048
+    rng = np.random.default_rng(9)
+    w = np.zeros((ny, nx // 2 + 1), dtype=np.complex128)
+    kk = 24
+    blk = rng.standard_normal((2 * kk + 1, kk + 1)) + 1j * rng.standard_normal((2 * kk + 1, kk + 1))
+    w[(np.arange(-kk, kk + 1) % ny)[:, None], np.arange(kk + 1)[None, :]] = 0.02 * blk
+    w[0, 0] = 0.0
+    col = w[:, 0].copy()
+    w[:, 0] = 0.5 * (col + np.conj(col[(-np.arange(ny)) % ny]))
+    one = nsb.NsbContext(nx, ny, Re=500.0, lib=emu_lib)
+    one.upload(nsb.OMEGA_HAT, w)
+    one.set_hyperviscosity(**HV)
+    one.step(0.0)
+    ref, dt_ref = one.download(nsb.OMEGA_HAT), one.state()[0]
+    one.close()
+    grp = nsb.NsbGroup(nx, ny, 2, devices=[0, 0], lib=emu_lib, Re=500.0)
+    grp.upload(nsb.OMEGA_HAT, w)
+    grp.each(lambda c: c.set_hyperviscosity(**HV))
+    parts = grp.each(lambda c: c.partition())
+    assert parts[0]["col1"] == parts[1]["col0"] and parts[1]["col1"] == 343 and parts[1]["row0"] == 1024
+    grp.step(0.0)
+    got = grp.download_omega_hat()
+    dts = grp.each(lambda c: c.state()[0])
+    grp.close()
+    assert np.array_equal(got, ref)
+    assert dts[0] == dts[1] == dt_ref

@@ -133,3 +133,51 @@ def test_chain_persistent_equals_plain_8192(nsb, cuda_lib, monkeypatch):
     for o in out[1:]:
         assert np.array_equal(o[0], out[0][0])
         assert o[1] == out[0][1]
+
+
+def _turbulence_block(n, seed, kk=64, amp=0.02):
+    rng = np.random.default_rng(seed)
+    w = np.zeros((n, n // 2 + 1), dtype=np.complex128)
+    blk = rng.standard_normal((2 * kk + 1, kk + 1)) + 1j * rng.standard_normal((2 * kk + 1, kk + 1))
+    w[(np.arange(-kk, kk + 1) % n)[:, None], np.arange(kk + 1)[None, :]] = amp * blk
+    w[0, 0] = 0.0
+    col = w[:, 0].copy()
+    w[:, 0] = 0.5 * (col + np.conj(col[(-np.arange(n)) % n]))
+    return w
+
+
+def _slab_vs_single(nsb, cuda_lib, n, world, devices, steps=3):
+    w = _turbulence_block(n, 21)
+    one = nsb.NsbContext(n, n, Re=1e4, lib=cuda_lib)
+    one.upload(nsb.OMEGA_HAT, w)
+    one.set_hyperviscosity(**HV)
+    for _ in range(steps):
+        one.step(0.0)
+    ref, st_ref = one.download(nsb.OMEGA_HAT), one.state()
+    one.close()
+    grp = nsb.NsbGroup(n, n, world, devices=devices, lib=cuda_lib, Re=1e4)
+    grp.upload(nsb.OMEGA_HAT, w)
+    grp.each(lambda c: c.set_hyperviscosity(**HV))
+    for _ in range(steps):
+        grp.step(0.0)
+    got = grp.download_omega_hat()
+    sts = grp.each(lambda c: c.state())
+    grp.close()
+    assert np.array_equal(got, ref)
+    for st in sts:
+        assert st == st_ref
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_decomposition_logical_devices(nsb, cuda_lib, world):
+    """SURVEY 8e on ONE GPU: `world` slab-decomposed contexts on device 0 (kx-column blocks in
+    spectral space, y-row blocks in physical space, both transposes as pushes into the owner's
+    buffers) must reproduce the single-context run bit for bit, including the adaptive dt."""
+    _slab_vs_single(nsb, cuda_lib, 2048, world, [0] * world)
+
+
+def test_slab_decomposition_two_gpus(nsb, cuda_lib):
+    """the same across two physical GPUs (NVLink peer stores); skipped on a 1-GPU box"""
+    if cuda_lib.nsb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _slab_vs_single(nsb, cuda_lib, 4096, 2, [0, 1])
