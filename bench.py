@@ -16,11 +16,15 @@ SURVEY.md 8d config 4 at N=1) over the whole grid. One JSON line is printed by r
   e2e_eager (extra) the strict drop-in loop `data->dt = ns_spectral_compute_cfl_timestep();
             ns_spectral_advance_rk4()` under NS_SYNC_EAGER: every array the reference
             touches crosses PCIe both ways each step.
-  roofline  dominant kernel (k_gamma) against the measured HBM peak in MEASURED_PEAKS.json:
-            algorithmic bytes per launch (SURVEY 8d stage (ii): read 4A + write 1A,
-            A = 16*nkx*ny bytes) / mean launch time from CUDA events on the launching
-            stream (nsb_profile_begin/_end), plus the whole-step figure at 512 B per
+  roofline  dominant kernel against the measured HBM peak in MEASURED_PEAKS.json:
+            algorithmic bytes per launch (16A per stage, A = 16*nkx*ny bytes, split
+            over the kernels of this decomposition) / mean launch time from CUDA events on the
+            launching stream (nsb_profile_begin/_end), plus the whole-step figure at 512 B per
             grid-point-step.
+  --gpus N  (torchrun, one rank per GPU) the SAME grid slab-decomposed over N GPUs (strong
+            scaling): kx-column blocks in spectral space, y-row blocks in physical space, the
+            FFT transposes as NVLink peer stores fused into the kernels; ranks exchange CUDA IPC
+            handles over the gloo group once, the data path uses no collective library.
   cpu_baseline  oracle/_ref (the unmodified reference sources + shim FFT; FFTW is not
             installable offline) timed on this box's host cores on a bounded sample.
 
@@ -230,6 +234,24 @@ def run_gpu_arm(args):
     host.ns_spectral_backend_context.restype = C.c_void_p
     host.ns_spectral_backend_context.argtypes = [C.c_void_p]
     ctx = C.c_void_p(host.ns_spectral_backend_context(s.sp))
+    if world > 1:
+        # slab decomposition: partition, then swap the CUDA IPC handles of T, T' and the scalar block
+        import torch
+        nsblib.nsb_mgpu_setup.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        nsblib.nsb_mgpu_export.argtypes = [C.c_void_p, C.c_char_p]
+        nsblib.nsb_mgpu_import.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+        if nsblib.nsb_mgpu_setup(ctx, rank, world) != 0:
+            raise SystemExit("bench.py: " + nsblib.nsb_last_error().decode())
+        buf = C.create_string_buffer(192)
+        if nsblib.nsb_mgpu_export(ctx, buf) != 0:
+            raise SystemExit("bench.py: " + nsblib.nsb_last_error().decode())
+        mine = torch.tensor(list(buf.raw), dtype=torch.uint8)
+        gathered = [torch.zeros(192, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        for peer in range(world):
+            if peer != rank and nsblib.nsb_mgpu_import(ctx, peer, bytes(gathered[peer].tolist())) != 0:
+                raise SystemExit("bench.py: " + nsblib.nsb_last_error().decode())
+        dist.barrier()
     blk, kk = synthetic_spectrum_block()
     w = s.arr("omega_hat")
     w[np.arange(-kk, kk + 1) % n, : kk + 1] = blk
@@ -240,7 +262,7 @@ def run_gpu_arm(args):
     cfg = orc.ForcingConfig()
     host.ns_forcing_config_default(C.byref(cfg))
     cfg.kmin, cfg.kmax, cfg.energy_target = FORCING["kmin"], FORCING["kmax"], FORCING["energy_target"]
-    cfg.correlation_time, cfg.seed, cfg.type = FORCING["tau"], FORCING["seed"] + rank, 0
+    cfg.correlation_time, cfg.seed, cfg.type = FORCING["tau"], FORCING["seed"], 0  # every rank replays the same stream
     fs = orc.ForcingState()
     assert host.ns_forcing_state_init(C.byref(fs), C.byref(cfg), s.s.k2, s.s.nkx, s.s.nky) == 0
     ib, jb = C.c_int(), C.c_int()
@@ -269,7 +291,7 @@ def run_gpu_arm(args):
     launches = nsblib.nsb_launch_count(ctx) - l0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = all_max(dist, ms.value / args.steps)
-    total_points = all_sum(dist, float(n) * n)       # replicas: every rank advances its own grid
+    total_points = float(n) * n                       # ONE grid, slab-decomposed over the ranks
     value = total_points / (ms_step * 1e-3)
 
     # ---- e2e: one step per call through the C entry points, forcing H2D + scalars D2H each step
@@ -292,38 +314,59 @@ def run_gpu_arm(args):
     kms = (C.c_double * 6)()
     kcnt = (C.c_int * 6)()
     nsblib.nsb_profile_end(ctx, kms, kcnt)
-    names = ["k_alpha_inv", "k_beta_inv", "k_gamma", "k_beta_fwd", "k_alpha_fwd", "other"]
-    per_kernel = {nm: {"launches": int(kcnt[k]), "ms_per_launch": (kms[k] / kcnt[k]) if kcnt[k] else None,
+    names = ["k_alpha1024<inv> (stage-1 spectral ops + inverse y FFT)", "k_chain_B_tma", "k_chain_G",
+             "k_chain_F", "k_alpha1024<fwd,inv> (forward y FFT + RK update + next inverse y FFT)", "other"]
+    if n <= 1024:
+        names = ["k_alpha1024<inv>", "k_beta_inv (unused)", "k_gamma1024", "k_beta_fwd (unused)",
+                 "k_alpha1024<fwd,inv>", "other"]
+    per_kernel = {nm: {"launches_per_step": int(kcnt[k]) // prof_steps,
+                       "ms_per_launch": (kms[k] / kcnt[k]) if kcnt[k] else None,
                        "ms_per_step": kms[k] / prof_steps} for k, nm in enumerate(names)}
     A = 16.0 * (n // 2 + 1) * n
     peak, peak_src = measured_peaks()
-    top = max(names[:5], key=lambda nm: per_kernel[nm]["ms_per_step"])
-    alg_bytes = {"k_alpha_inv": 5 * A, "k_beta_inv": 8 * A, "k_gamma": 5 * A, "k_beta_fwd": 2 * A,
-                 "k_alpha_fwd": 6 * A}
-    # SURVEY 8d contract: 16A per stage split over the kernels of this decomposition:
-    # (i) spectral + inverse y pass 1A in / 4A out; (ii) inverse x + Jacobian + forward x 4A in /
-    # 1A out; (iii) forward y pass + RK 4A in / 2A out. The beta kernels are extra passes the
-    # model does not grant; they are charged at their own in+out arrays for reference only.
+    top_i = max(range(5), key=lambda k: kms[k])
+    top = names[top_i]
+    # SURVEY 8d contract: 16A per stage = 64A per step, A = 16*nkx*ny bytes (full, unpruned arrays):
+    # (i) spectral ops + inverse y pass 1A in / 4A out; (ii) inverse x + Jacobian + forward x 4A in /
+    # 1A out; (iii) forward y pass + RK 4A in / 2A out. Per step and kernel kind of this decomposition:
+    # stage-1 alpha_inv = (i) = 5A; fused alpha = 3 x [(iii)+(i)] + 1 x (iii) = 39A; G = 4 x (ii) = 20A.
+    # B and F are passes the model does not grant; they are charged at their own in+out arrays
+    # (4 x 8A, 4 x 2A) for reference only. Each rank moves 1/world of these bytes.
+    alg_step = [5 * A, 32 * A, 20 * A, 8 * A, 39 * A]
+    top_launches = max(1, int(kcnt[top_i]) // prof_steps)
+    alg_launch = alg_step[top_i] / top_launches / world
     tl = per_kernel[top]["ms_per_launch"]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:
         try:
-            traffic = json.load(open(tpath)).get(str(n), {}).get(top)
+            traffic = json.load(open(tpath)).get(str(n), {}).get(str(top_i))
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": top, "achieved": alg_bytes[top] / (tl * 1e-3) / 1e9, "peak": peak,
-                "unit": "GB/s", "frac": alg_bytes[top] / (tl * 1e-3) / 1e9 / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[top],
+    roofline = {"bound": "hbm", "kernel": top, "achieved": alg_launch / (tl * 1e-3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": alg_launch / (tl * 1e-3) / 1e9 / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_launch,
                 "ms_per_launch": tl,
                 "step": {"algorithmic_bytes_per_grid_point_step": 512,
-                         "achieved": 512.0 * (float(n) * n / (ms.value / args.steps * 1e-3)) / 1e9,
-                         "frac": 512.0 * (float(n) * n / (ms.value / args.steps * 1e-3)) / 1e9 / peak},
+                         "achieved": 512.0 * (float(n) * n / (ms_step * 1e-3)) / 1e9 / world,
+                         "frac": 512.0 * (float(n) * n / (ms_step * 1e-3)) / 1e9 / world / peak,
+                         "note": "per GPU: 512 B x grid-point-steps/s / n_gpus against one GPU's HBM peak"},
                 "per_kernel": per_kernel}
+    if world > 1:
+        # NVLink: every stage pushes 4 T fields + 1 T' field of the retained columns; (world-1)/world of
+        # a rank's share leaves the GPU. SURVEY 8e contract figure (unpruned) alongside the real bytes.
+        ncol = (2 * (n // 2 + 1)) // 3 + 1
+        real = 4 * 5 * (16.0 * ncol * n / world) * (world - 1) / world
+        contract = 20 * (A / world) * (world - 1) / world
+        roofline["nvlink"] = {"bytes_sent_per_gpu_per_step": real, "contract_bytes_per_gpu_per_step": contract,
+                              "achieved_GBs": real / (ms_step * 1e-3) / 1e9,
+                              "contract_GBs": contract / (ms_step * 1e-3) / 1e9,
+                              "peak_GBs": 770.0, "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
+                              "frac": contract / (ms_step * 1e-3) / 1e9 / 770.0}
 
-    # ---- strict drop-in loop (EAGER): bounded, rank 0 only, small step count
+    # ---- strict drop-in loop (EAGER): bounded, single GPU only, small step count
     e2e_eager = None
-    if rank == 0 and args.eager_steps > 0:
+    if world == 1 and args.eager_steps > 0:
         host.ns_spectral_set_sync_policy(s.sp, 0)
         t0 = time.perf_counter()
         for _ in range(args.eager_steps):
@@ -348,13 +391,14 @@ def run_gpu_arm(args):
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"forced 2-D turbulence {n}x{n} FP64, hyperviscosity + white forcing, adaptive CFL "
                                    f"dt (BASELINE config {'4' if n == 16384 else '3' if n == 4096 else 'n=' + str(n)})",
                        "Re": RE, "hyperviscosity": HV, "forcing": {"type": "white", **FORCING},
                        "init": "random-phase spectrum k^2 exp(-(k/8)^2), max|omega| = 5",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (slab decomposition "
-                                                                   "across GPUs not built yet)",
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"slab decomposition over {world} GPUs: kx-column blocks / y-row blocks, FFT transposes as "
+                       "NVLink peer stores fused into the kernels (one process per GPU, CUDA IPC)",
                        "plan": {"Y1": plan[0], "Y2": plan[1], "X1": plan[2], "X2": plan[3]},
                        "l2": "inputs larger than L2: working set >> 126 MB at this size, no flush needed"
                              if n >= 2048 else "working set fits L2 at this size"},
