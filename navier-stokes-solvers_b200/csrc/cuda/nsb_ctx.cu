@@ -76,6 +76,7 @@ struct nsb_ctx {
     cd *chZ, *chP;     /* L2-resident rings of the persistent kernel */
     unsigned *chCtr;   /* ticket + per-slab completion counters */
     int ch_slotZ, ch_slotP, ch_leadG, ch_leadF, ch_ctas, ch_btma;
+    int alpha_cols; /* columns per CTA of the fused column kernel: 4 (two CTAs per SM) or 8 */
     nsb_tmap tmT; /* tensor map of T in bufA (TMA-fed B) */
     int tmT_ok;
     /* slab decomposition over the devices of one NVSwitch domain */
@@ -245,6 +246,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->ch_leadF = env_int("NSB_CHAIN_LEAD_F", 8);
     c->ch_ctas = env_int("NSB_CHAIN_CTAS", 2) == 2 ? 2 : 1;
     c->ch_btma = env_int("NSB_CHAIN_BTMA", 1);
+    c->alpha_cols = env_int("NSB_ALPHA_COLS", 4) == 8 ? 8 : 4;
     if (c->ch_leadG < 1) c->ch_leadG = 1;
     if (c->ch_leadF < 1) c->ch_leadF = 1;
     if (c->ch_slotZ <= c->ch_leadG) c->ch_slotZ = c->ch_leadG + 1;
@@ -703,22 +705,20 @@ static void fill_alpha_fast(nsb_ctx *c, AlphaFastArgs &fa, const cd *tp, int tp_
 
 static int launch_alpha1024(nsb_ctx *c, bool fwd, bool inv, const AlphaFastArgs &a) {
     const NsbGeom &g = c->g;
-    const dim3 grid((a.c1 - a.c0 + NSB_A1024_COLS - 1) / NSB_A1024_COLS, g.Y2), block(128);
-    const size_t smem = NSB_A1024_SMEM;
     prof_pre(c, fwd ? PK_ALPHA_FWD : PK_ALPHA_INV);
-    if (fwd && inv) {
-        auto k = k_alpha1024<true, true>;
-        if (ensure_smem(c, k, smem)) return -1;
-        NSB_LAUNCH(k, grid, block, smem, c->stream, g, a);
-    } else if (fwd) {
-        auto k = k_alpha1024<true, false>;
-        if (ensure_smem(c, k, smem)) return -1;
-        NSB_LAUNCH(k, grid, block, smem, c->stream, g, a);
-    } else {
-        auto k = k_alpha1024<false, true>;
-        if (ensure_smem(c, k, smem)) return -1;
-        NSB_LAUNCH(k, grid, block, smem, c->stream, g, a);
+#define NSB_A1024(F, I, COLS)                                                                   \
+    {                                                                                           \
+        auto k = k_alpha1024<F, I, COLS>;                                                       \
+        const dim3 grid((a.c1 - a.c0 + COLS - 1) / COLS, g.Y2), block(COLS * 32);               \
+        if (ensure_smem(c, k, NSB_A1024_SMEM(COLS))) return -1;                                 \
+        NSB_LAUNCH(k, grid, block, NSB_A1024_SMEM(COLS), c->stream, g, a);                      \
     }
+    if (c->alpha_cols == 8) {
+        if (fwd && inv) NSB_A1024(true, true, 8) else if (fwd) NSB_A1024(true, false, 8) else NSB_A1024(false, true, 8)
+    } else {
+        if (fwd && inv) NSB_A1024(true, true, 4) else if (fwd) NSB_A1024(true, false, 4) else NSB_A1024(false, true, 4)
+    }
+#undef NSB_A1024
     prof_post(c);
     CKL();
     c->launches++;
@@ -1521,6 +1521,9 @@ extern "C" int nsb_mgpu_setup(nsb_ctx *c, int rank, int world) {
     c->tmT_ok = 0;
     c->mg_ipc = 0;
     c->mg_epoch = 0;
+    /* measured on 2 B200s: 128-byte peer stores (8 columns per CTA) beat 64-byte ones by ~25 % in the
+     * column kernel; on one device two 4-column CTAs per SM are slightly faster */
+    if (!getenv("NSB_ALPHA_COLS")) c->alpha_cols = world > 1 ? 8 : 4;
     CK(cudaMemset(c->d_sc->peer_flags, 0, sizeof(c->d_sc->peer_flags)));
     return 0;
 }

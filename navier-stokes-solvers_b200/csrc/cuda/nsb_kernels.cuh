@@ -960,16 +960,19 @@ struct AlphaFastArgs {
     NsbRk rk;        /* K-layout pointers */
 };
 
-#define NSB_A1024_COLS 4
-#define NSB_A1024_SMEM (1024 * 16 + 1024 * NSB_A1024_COLS * 16 + 32 * 16 + 1024 * 8)
+#define NSB_A1024_COLS 4 /* granularity of the column partition; kernels take 4 or 8 columns per CTA */
+#define NSB_A1024_SMEM(COLS) (1024 * 16 + 1024 * (COLS) * 16 + 32 * 16 + 1024 * 8)
 
 /* shared tile S[1024 rows][4 columns], 16-byte chunks XOR-swizzled so that row-wise
  * (cooperative, coalesced) and column-wise (per-warp FFT) accesses are both conflict free */
-__device__ __forceinline__ int nsb_sidx(int row, int c) { return row * NSB_A1024_COLS + (c ^ ((row >> 1) & 3)); }
+template <int COLS>
+__device__ __forceinline__ int nsb_sidx(int row, int c) {
+    return COLS == 4 ? row * 4 + (c ^ ((row >> 1) & 3)) : row * COLS + (c ^ (row & (COLS - 1)));
+}
 
 /* warp FFT-1024 whose transpose goes through the warp's own column of S (skewed so the
  * strided read is conflict free as well) */
-template <bool INV>
+template <bool INV, int COLS>
 __device__ __forceinline__ void nsb_fft1024_warp_col(cd (&x)[32], cd *S, int col, const cd *TW, int lane) {
     nsb_dft32<INV>(x);
 #pragma unroll
@@ -978,10 +981,10 @@ __device__ __forceinline__ void nsb_fft1024_warp_col(cd (&x)[32], cd *S, int col
         x[r] = INV ? cmulc(x[r], tw) : cmul(x[r], tw);
     }
 #pragma unroll
-    for (int r = 0; r < 32; ++r) S[nsb_sidx(32 * r + ((lane + r) & 31), col)] = x[r];
+    for (int r = 0; r < 32; ++r) S[nsb_sidx<COLS>(32 * r + ((lane + r) & 31), col)] = x[r];
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 32; ++q) x[q] = S[nsb_sidx(32 * lane + ((q + lane) & 31), col)];
+    for (int q = 0; q < 32; ++q) x[q] = S[nsb_sidx<COLS>(32 * lane + ((q + lane) & 31), col)];
     __syncwarp();
     nsb_dft32<INV>(x);
 }
@@ -1010,17 +1013,17 @@ __device__ NSB_NOINLINE cd nsb_rk_update_call(const NsbRk *r, size_t idx, double
  *                y twiddle -> tile -> cooperative coalesced store to T[f]
  * Replaces k_alpha_fwd<RK> of stage s followed by k_alpha_inv<STEP> of stage s+1.
  */
-template <bool FWD, bool INV>
-__global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a) {
+template <bool FWD, bool INV, int COLS>
+__global__ void __launch_bounds__(COLS * 32, 8 / COLS) k_alpha1024(NsbGeom g, AlphaFastArgs a) {
     NSB_DYN_SMEM(cd, smem);
     cd *TW = smem;
     cd *S = smem + 1024;
-    cd *TB = S + 1024 * NSB_A1024_COLS; /* TB[m] = exp(-2 pi i (32 j2 m)/ny) */
+    cd *TB = S + 1024 * COLS; /* TB[m] = exp(-2 pi i (32 j2 m)/ny) */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j2 = blockIdx.y, ic0 = a.c0 + blockIdx.x * NSB_A1024_COLS;
+    const int j2 = blockIdx.y, ic0 = a.c0 + blockIdx.x * COLS;
     const int ic = ic0 + warp;
     const bool active = ic < a.c1;
-    const int cc = threadIdx.x & 3, rr = threadIdx.x >> 2; /* cooperative copies: 4 threads per row */
+    const int cc = threadIdx.x & (COLS - 1), rr = threadIdx.x / COLS; /* cooperative copies: COLS threads per row */
     nsb_fill_tw1024(TW, g.WY, g.ny / 1024);
     if (threadIdx.x < 32) TB[threadIdx.x] = __ldg(&g.WY[(size_t)32 * j2 * threadIdx.x]);
     /* y twiddle exp(-2 pi i j2 y1/ny), y1 = lane + 32 m, factored as ta * TB[m] */
@@ -1037,7 +1040,7 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
             const int row = rr + 32 * i;
             cd v = cmk(0.0, 0.0);
             if (colok) v = a.in[(size_t)(row * g.Y2 + j2) * a.in_pitch + (ic0 - a.c0) + cc];
-            S[nsb_sidx(row, cc)] = v;
+            S[nsb_sidx<COLS>(row, cc)] = v;
         }
     }
     __syncthreads();
@@ -1049,7 +1052,7 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
             if (job == 0) {
 #pragma unroll
                 for (int m = 0; m < 32; ++m) {
-                    cd v = S[nsb_sidx(lane + 32 * m, warp)];
+                    cd v = S[nsb_sidx<COLS>(lane + 32 * m, warp)];
                     if (g.Y2 > 1) v = cmul(v, cmul(ta, TB[m]));
                     x[m] = cmk(v.x, -v.y); /* forward = conj o inverse o conj */
                 }
@@ -1079,16 +1082,16 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
                     x[m] = keep ? v : cmk(0.0, 0.0);
                 }
             }
-            nsb_fft1024_warp_col<true>(x, S, warp, TW, lane);
+            nsb_fft1024_warp_col<true, COLS>(x, S, warp, TW, lane);
             if (job == 0) {
 #pragma unroll
-                for (int m = 0; m < 32; ++m) S[nsb_sidx(lane + 32 * m, warp)] = cmk(x[m].x, -x[m].y);
+                for (int m = 0; m < 32; ++m) S[nsb_sidx<COLS>(lane + 32 * m, warp)] = cmk(x[m].x, -x[m].y);
             } else {
 #pragma unroll
                 for (int m = 0; m < 32; ++m) {
                     cd v = x[m];
                     if (g.Y2 > 1) v = cmulc(v, cmul(ta, TB[m]));
-                    S[nsb_sidx(lane + 32 * m, warp)] = v;
+                    S[nsb_sidx<COLS>(lane + 32 * m, warp)] = v;
                 }
                 /* registers are free until the next transform: fetch its input now so the
                  * latency hides behind the barrier and the cooperative store of this tile */
@@ -1101,7 +1104,7 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
         }
         __syncthreads();
         if (job == 0) {
-            /* RK sweep: thread takes elements flat = tid + 128 i of the 4 x 1024 tile, four at a
+            /* RK sweep: thread takes elements flat = tid + 32*COLS*i of the COLS x 1024 tile, four at a
              * time with all state loads issued before the arithmetic */
             const double dt = *a.rk.dt;
             const bool use_sfd = a.rk.hv.sfd != 0;
@@ -1111,7 +1114,7 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
                 size_t kid[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int flat = threadIdx.x + 128 * (i0 + u);
+                    const int flat = threadIdx.x + (32 * COLS) * (i0 + u);
                     const int c = flat >> 10, j1 = flat & 1023;
                     int icc = ic0 + c;
                     if (icc >= a.c1) icc = a.c1 - 1; /* clamped: loaded, never stored */
@@ -1123,12 +1126,12 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int flat = threadIdx.x + 128 * (i0 + u);
+                    const int flat = threadIdx.x + (32 * COLS) * (i0 + u);
                     const int c = flat >> 10, j1 = flat & 1023;
                     const int icc = ic0 + c;
                     const int band = nsb_band(j1 * g.Y2 + j2, g.ny);
                     if (icc < a.c1 && nsb_iabs(band) <= g.ycut) {
-                        const cd v = S[nsb_sidx(j1, c)];
+                        const cd v = S[nsb_sidx<COLS>(j1, c)];
                         const cd Nh = cmk(-(v.x * g.norm), -(v.y * g.norm));
                         cd acc, sfd;
                         const cd nxt = nsb_rk_math(a.rk, dt, W0v[u], Wsv[u], ACv[u], SFv[u], __ldg(&g.kx[icc]), KY[j1],
@@ -1152,7 +1155,7 @@ __global__ void __launch_bounds__(128, 2) k_alpha1024(NsbGeom g, AlphaFastArgs a
                     const int row = rr + 32 * i;
                     const int y = row * g.Y2 + j2;
                     /* the device that owns row y receives it (local store or NVLink peer store) */
-                    a.outp[y >> a.row_shift][fo + (size_t)(y & rmask) * a.out_pitch] = S[nsb_sidx(row, cc)];
+                    a.outp[y >> a.row_shift][fo + (size_t)(y & rmask) * a.out_pitch] = S[nsb_sidx<COLS>(row, cc)];
                 }
             }
         }
