@@ -960,6 +960,16 @@ struct AlphaFastArgs {
     NsbRk rk;        /* K-layout pointers */
 };
 
+/* modes per thread and round of the RK sweep: all their state loads are in flight together (the
+ * transform registers are idle during the sweep, so there is room for 8 x 3 complex values) */
+#ifndef NSB_RK_BATCH
+#define NSB_RK_BATCH 4 /* measured: 8 (and telling the allocator x is dead during the sweep) is 20 % slower */
+#endif
+#ifndef NSB_TILE_UNROLL
+#define NSB_TILE_UNROLL 8
+#endif
+#define NSB_PRAGMA_(x) _Pragma(#x)
+#define NSB_UNROLL(n) NSB_PRAGMA_(unroll n)
 #define NSB_A1024_COLS 4 /* granularity of the column partition; kernels take 4 or 8 columns per CTA */
 #define NSB_A1024_SMEM(COLS) (1024 * 16 + 1024 * (COLS) * 16 + 32 * 16 + 1024 * 8)
 
@@ -1035,7 +1045,7 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS) k_alpha1024(NsbGeom g, Al
     const cd *Wre = FWD ? a.rk.Wst : a.Wsrc; /* state the inverse fields derive from */
     if (FWD) {
         const bool colok = ic0 + cc < a.c1;
-#pragma unroll 8
+        NSB_UNROLL(NSB_TILE_UNROLL)
         for (int i = 0; i < 32; ++i) {
             const int row = rr + 32 * i;
             cd v = cmk(0.0, 0.0);
@@ -1109,11 +1119,11 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS) k_alpha1024(NsbGeom g, Al
             const double dt = *a.rk.dt;
             const bool use_sfd = a.rk.hv.sfd != 0;
 #pragma unroll 1
-            for (int i0 = 0; i0 < 32; i0 += 4) {
-                cd W0v[4], Wsv[4], ACv[4], SFv[4];
-                size_t kid[4];
+            for (int i0 = 0; i0 < 32; i0 += NSB_RK_BATCH) {
+                cd W0v[NSB_RK_BATCH], Wsv[NSB_RK_BATCH], ACv[NSB_RK_BATCH], SFv[NSB_RK_BATCH];
+                size_t kid[NSB_RK_BATCH];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < NSB_RK_BATCH; ++u) {
                     const int flat = threadIdx.x + (32 * COLS) * (i0 + u);
                     const int c = flat >> 10, j1 = flat & 1023;
                     int icc = ic0 + c;
@@ -1125,7 +1135,7 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS) k_alpha1024(NsbGeom g, Al
                     SFv[u] = use_sfd ? a.rk.SFD[kid[u]] : cmk(0.0, 0.0);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < NSB_RK_BATCH; ++u) {
                     const int flat = threadIdx.x + (32 * COLS) * (i0 + u);
                     const int c = flat >> 10, j1 = flat & 1023;
                     const int icc = ic0 + c;

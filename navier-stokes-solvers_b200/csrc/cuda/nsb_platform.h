@@ -84,6 +84,7 @@ static inline void nsb_mbar_wait(nsb_mbar_t *bar, unsigned parity) {
     while (((unsigned)(*bar) & 1u) == parity) nsbemu::yield();
 }
 static inline void nsb_fence_proxy_async() {}
+static inline unsigned nsb_smem_align_pad(const void *p, unsigned a) { return (unsigned)((a - ((size_t)p & (a - 1))) & (a - 1)); }
 #else
 typedef unsigned long long nsb_mbar_t;
 __device__ __forceinline__ unsigned nsb_smem_addr(const void *p) {
@@ -118,6 +119,10 @@ __device__ __forceinline__ void nsb_mbar_wait(nsb_mbar_t *bar, unsigned parity) 
 }
 __device__ __forceinline__ void nsb_fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+/* bytes to add to a shared-memory pointer to reach the next multiple of `a` (a power of two) */
+__device__ __forceinline__ unsigned nsb_smem_align_pad(const void *p, unsigned a) {
+    return (a - (nsb_smem_addr(p) & (a - 1))) & (a - 1);
 }
 #endif
 

@@ -10,7 +10,8 @@ from tools.quick_perf import spectrum
 nsb = ge.load_package()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-c = nsb.NsbContext(n, n, Re=1e4)
+lib = nsb.load_nsb(os.environ.get("NSB_LIB_OVERRIDE"))  # dev aid: alternative builds of libnsb.so
+c = nsb.NsbContext(n, n, Re=1e4, lib=lib)
 c.upload(nsb.OMEGA_HAT, spectrum(n))
 c.set_hyperviscosity(1, 5.0, 4, 0.3)
 for _ in range(2):
