@@ -498,7 +498,8 @@ __device__ __forceinline__ void chain_B_step2x(const NsbGeom &g, const ChainArgs
  * is off the critical path with one CTA per SM.
  * smem: 2 stages x (2*16*nseg*BC complex) + 2 mbarriers (+128 B alignment slack).
  */
-__global__ void __launch_bounds__(256, 1) k_chain_B_tma(NsbGeom g, ChainArgs a, const NSB_GRID_CONSTANT nsb_tmap tmT) {
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a, const NSB_GRID_CONSTANT nsb_tmap tmT) {
     NSB_DYN_SMEM(cd, smem_raw);
     /* 128-byte alignment for the TMA destination. (Measured: keeping shared-memory provenance, i.e.
      * LDS/STS instead of the generic LD/ST this cast produces, made the kernel 7 % SLOWER.) */

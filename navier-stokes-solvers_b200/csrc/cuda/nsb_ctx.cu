@@ -77,8 +77,9 @@ struct nsb_ctx {
     unsigned *chCtr;   /* ticket + per-slab completion counters */
     int ch_slotZ, ch_slotP, ch_leadG, ch_leadF, ch_ctas, ch_btma;
     int alpha_cols; /* columns per CTA of the fused column kernel: 4 (two CTAs per SM) or 8 */
-    nsb_tmap tmT; /* tensor map of T in bufA (TMA-fed B) */
-    int tmT_ok;
+    nsb_tmap tmT, tmT8; /* tensor maps of T in bufA (TMA-fed B), 16- and 8-column boxes */
+    int tmT_ok, tmT8_ok;
+    int ch_bbc;
     /* slab decomposition over the devices of one NVSwitch domain */
     int mg_rank, mg_world;
     int mg_cb, mg_c0, mg_c1;     /* columns per device, own column range */
@@ -233,6 +234,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->k_truth = 0;
     c->chZ = c->chP = nullptr;
     c->tmT_ok = 0;
+    c->tmT8_ok = 0;
     c->chCtr = nullptr;
     c->chain_mode = 0;
     if (c->fast && g.X2 == 1024 && c->has_beta && g.ny % NSB_CH_ROWS == 0 && g.Y2 <= NSB_CH_ROWS &&
@@ -246,6 +248,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->ch_leadF = env_int("NSB_CHAIN_LEAD_F", 8);
     c->ch_ctas = env_int("NSB_CHAIN_CTAS", 2) == 2 ? 2 : 1;
     c->ch_btma = env_int("NSB_CHAIN_BTMA", 1);
+    c->ch_bbc = env_int("NSB_CHAIN_BBC", -1);
     c->alpha_cols = env_int("NSB_ALPHA_COLS", 4) == 8 ? 8 : 4;
     if (c->ch_leadG < 1) c->ch_leadG = 1;
     if (c->ch_leadF < 1) c->ch_leadF = 1;
@@ -832,18 +835,38 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
         a.Z = c->bufB;
         a.P = c->bufA;
         if (c->ch_btma && 2 * tileB + 64 + 128 + twtab <= 227 * 1024 && 2 * g.BC <= 256) {
-            /* persistent, TMA-fed B: one CTA per SM, two shared-memory stages */
-            auto k = k_chain_B_tma;
-            const size_t smemB = 2 * tileB + 64 + 128 + twtab;
-            if (ensure_smem(c, k, smemB, true)) return -1;
-            if (!c->tmT_ok) {
-                if (make_tmap_2d(&c->tmT, c->bufA, (size_t)2 * g.PT, (size_t)4 * c->mg_rows, (size_t)g.PT * sizeof(cd),
-                                 2 * g.BC, NSB_CH_ROWS))
+            /* persistent, TMA-fed B: two shared-memory stages per CTA. With 8-column batches two
+             * 128-thread CTAs share an SM (each with the full register budget), so one CTA's
+             * step 1 overlaps the other's step 2 */
+            NsbGeom gB = g;
+            ChainArgs aB = a;
+            /* measured: 8-column batches win while the tile is small (4096^2: 0.31 vs 0.40 ms), 16-column
+             * batches with one 256-thread CTA per SM win at 16384^2 (3.56 vs 5.58 ms) */
+            const bool half = g.BC == 16 && (c->ch_bbc == 8 || (c->ch_bbc < 0 && tileB <= 48 * 1024));
+            if (half) {
+                gB.BC = 8;
+                aB.nbatch = (g.X2h + 1 + 7) / 8;
+            }
+            const size_t tB = half ? tileB / 2 : tileB;
+            const size_t smemB = 2 * tB + 64 + 128 + (half ? twtab / 2 : twtab);
+            nsb_tmap *tm = half ? &c->tmT8 : &c->tmT;
+            int *tm_ok = half ? &c->tmT8_ok : &c->tmT_ok;
+            if (!*tm_ok) {
+                if (make_tmap_2d(tm, c->bufA, (size_t)2 * g.PT, (size_t)4 * c->mg_rows, (size_t)g.PT * sizeof(cd),
+                                 2 * gB.BC, NSB_CH_ROWS))
                     return -1;
-                c->tmT_ok = 1;
+                *tm_ok = 1;
             }
             prof_pre(c, PK_BETA_INV);
-            NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), smemB, c->stream, g, a, c->tmT);
+            if (half) {
+                auto k = k_chain_B_tma<128, 2>;
+                if (ensure_smem(c, k, smemB, true)) return -1;
+                NSB_LAUNCH(k, dim3(2 * c->sm_count), dim3(128), smemB, c->stream, gB, aB, *tm);
+            } else {
+                auto k = k_chain_B_tma<256, 1>;
+                if (ensure_smem(c, k, smemB, true)) return -1;
+                NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), smemB, c->stream, gB, aB, *tm);
+            }
             prof_post(c);
             CKL();
             c->launches++;
@@ -1519,6 +1542,7 @@ extern "C" int nsb_mgpu_setup(nsb_ctx *c, int rank, int world) {
     c->mg_T[rank] = c->bufA; c->mg_Tp[rank] = c->bufTp; c->mg_sc[rank] = c->d_sc;
     if (world == 1) { c->mg_T[0] = c->bufA; c->mg_Tp[0] = c->bufTp; c->mg_sc[0] = c->d_sc; }
     c->tmT_ok = 0;
+    c->tmT8_ok = 0;
     c->mg_ipc = 0;
     c->mg_epoch = 0;
     /* measured on 2 B200s: 128-byte peer stores (8 columns per CTA) beat 64-byte ones by ~25 % in the

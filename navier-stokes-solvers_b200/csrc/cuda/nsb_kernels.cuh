@@ -1056,6 +1056,12 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS) k_alpha1024(NsbGeom g, Al
     __syncthreads();
     cd x[32];
     bool prefetched = false;
+    /* rows of this lane that survive the 2/3 mask, one bit per register index (same for every job) */
+    unsigned keepmask = 0u;
+#pragma unroll
+    for (int m = 0; m < 32; ++m)
+        if (nsb_iabs(nsb_band((lane + 32 * m) * g.Y2 + j2, g.ny)) <= g.ycut) keepmask |= 1u << m;
+    const double kx2 = __dmul_rn(kxv, kxv);
 #pragma unroll 1
     for (int job = FWD ? 0 : 1; job <= (INV ? 4 : 0); ++job) {
         if (active) {
@@ -1078,18 +1084,18 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS) k_alpha1024(NsbGeom g, Al
 #pragma unroll
                 for (int m = 0; m < 32; ++m) {
                     const int j1 = lane + 32 * m;
-                    const bool keep = nsb_iabs(nsb_band(j1 * g.Y2 + j2, g.ny)) <= g.ycut;
                     const double kyv = KY[j1];
                     /* i k psi = -i (k/k^2) w for f < 2, i k w otherwise: one reciprocal per mode
                      * instead of the reference's two divisions (spectral_core.c:17,66); differs
                      * from it by <= 2 ulp, far inside the 1e-11 parity tolerance */
                     double kk = (f & 1) ? kyv : kxv;
                     if (f < 2) {
-                        const double k2 = __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv));
+                        const double k2 = __dadd_rn(kx2, __dmul_rn(kyv, kyv));
                         kk = (k2 > 1e-12) ? -(kk * nsb_drcp(k2)) : 0.0;
                     }
-                    const cd v = nsb_ik(kk, x[m]);
-                    x[m] = keep ? v : cmk(0.0, 0.0);
+                    /* 2/3 mask folded into the real factor (bit m of keepmask: row j1 is retained) */
+                    kk = ((keepmask >> m) & 1u) ? kk : 0.0;
+                    x[m] = nsb_ik(kk, x[m]);
                 }
             }
             nsb_fft1024_warp_col<true, COLS>(x, S, warp, TW, lane);
