@@ -1036,7 +1036,8 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS) k_alpha1024(NsbGeom g, Al
     const int cc = threadIdx.x & (COLS - 1), rr = threadIdx.x / COLS; /* cooperative copies: COLS threads per row */
     nsb_fill_tw1024(TW, g.WY, g.ny / 1024);
     if (threadIdx.x < 32) TB[threadIdx.x] = __ldg(&g.WY[(size_t)32 * j2 * threadIdx.x]);
-    /* y twiddle exp(-2 pi i j2 y1/ny), y1 = lane + 32 m, factored as ta * TB[m] */
+    /* y twiddle exp(-2 pi i j2 y1/ny), y1 = lane + 32 m, factored as ta * TB[m] (measured: a full
+     * 1024-entry table in shared memory costs more in lost L1 than the extra complex multiply) */
     const cd ta = __ldg(&g.WY[(size_t)j2 * lane]);
     double *KY = reinterpret_cast<double *>(TB + 32); /* ky of this CTA's rows, indexed by j1 */
     for (int k = threadIdx.x; k < 1024; k += blockDim.x) KY[k] = __ldg(&g.kyK[(size_t)j2 * 1024 + k]);
