@@ -176,8 +176,21 @@ def test_slab_decomposition_logical_devices(nsb, cuda_lib, world):
     _slab_vs_single(nsb, cuda_lib, 2048, world, [0] * world)
 
 
+def test_slab_decomposition_8192_four_logical_devices(nsb, cuda_lib):
+    """closer to the BASELINE scaling config (Y2 = X1 = 8): 8192^2 over 4 logical devices"""
+    _slab_vs_single(nsb, cuda_lib, 8192, 4, [0] * 4, steps=2)
+
+
 def test_slab_decomposition_two_gpus(nsb, cuda_lib):
     """the same across two physical GPUs (NVLink peer stores); skipped on a 1-GPU box"""
     if cuda_lib.nsb_device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _slab_vs_single(nsb, cuda_lib, 4096, 2, [0, 1])
+
+
+def test_free_running_fast_path_2048(nsb, cuda_lib, oracles):
+    """north-star drift bound on the FAST path (k_alpha1024 + chain kernels, K-layout state):
+    200 free-running forced steps at 2048^2, each side with its own adaptive dt; E and
+    enstrophy within 1e-9 relative (observed ~1e-13)."""
+    pc.check_free_running(nsb, cuda_lib, oracles, best_oracle_kind(oracles), 2048, 2048, 200, every=20, hv=HV,
+                          forcing=dict(kind="white"), Re=1e4)
