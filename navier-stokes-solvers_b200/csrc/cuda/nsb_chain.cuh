@@ -167,30 +167,6 @@ __device__ __forceinline__ void chain_B_item(const NsbGeom &g, const ChainArgs &
 #define NSB_CHG_WARP_BYTES(UMAX) (8192 + 16384 + ((UMAX) ? 8192 : 0))
 #define NSB_CH_TW_BYTES (1024 * 16)
 
-/* warp FFT-1024 (nsb_fft1024.cuh) with an unpadded, XOR-swizzled 8 KB transpose buffer */
-template <bool INV>
-__device__ __forceinline__ void nsb_fft1024_warp_sw(cd (&x)[32], double *T, const cd *TW, int lane) {
-    nsb_dft32<INV>(x);
-#pragma unroll
-    for (int r = 1; r < 32; ++r) {
-        const cd tw = TW[r * 32 + lane];
-        x[r] = INV ? cmulc(x[r], tw) : cmul(x[r], tw);
-    }
-#pragma unroll
-    for (int r = 0; r < 32; ++r) T[r * 32 + (lane ^ r)] = x[r].x;
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < 32; ++q) x[q].x = T[lane * 32 + (q ^ lane)];
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 32; ++r) T[r * 32 + (lane ^ r)] = x[r].y;
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < 32; ++q) x[q].y = T[lane * 32 + (q ^ lane)];
-    __syncwarp();
-    nsb_dft32<INV>(x);
-}
-
 /* one comb pair by one warp. wb: this warp's NSB_CHG_WARP_BYTES; returns max |u|^2 seen */
 template <bool UMAX>
 __device__ __forceinline__ double chain_G_pair(const cd *z1base, const cd *z2base, cd *pout, unsigned char *wb,

@@ -77,6 +77,9 @@ struct nsb_ctx {
     unsigned *chCtr;   /* ticket + per-slab completion counters */
     int ch_slotZ, ch_slotP, ch_leadG, ch_leadF, ch_ctas, ch_btma;
     int alpha_cols; /* columns per CTA of the fused column kernel: 4 (two CTAs per SM) or 8 */
+    int alpha_tma;  /* tile stores of the column kernel through TMA (8 columns per CTA, 128B swizzle) */
+    NsbTmaps tmA;   /* tensor maps of every device's T for those stores */
+    int tmA_ok;
     nsb_tmap tmT, tmT8; /* tensor maps of T in bufA (TMA-fed B), 16- and 8-column boxes */
     int tmT_ok, tmT8_ok;
     int ch_bbc;
@@ -250,6 +253,8 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->ch_btma = env_int("NSB_CHAIN_BTMA", 1);
     c->ch_bbc = env_int("NSB_CHAIN_BBC", -1);
     c->alpha_cols = env_int("NSB_ALPHA_COLS", 4) == 8 ? 8 : 4;
+    c->alpha_tma = env_int("NSB_ALPHA_TMA", 1);
+    c->tmA_ok = 0;
     if (c->ch_leadG < 1) c->ch_leadG = 1;
     if (c->ch_leadF < 1) c->ch_leadF = 1;
     if (c->ch_slotZ <= c->ch_leadG) c->ch_slotZ = c->ch_leadG + 1;
@@ -693,6 +698,36 @@ static int launch_beta(nsb_ctx *c, bool inverse, const BetaArgs &a) {
     return fail("unsupported Y2=%d", c->g.Y2);
 }
 
+/* 3-D FP64 tensor map {dim0 doubles, dim1, dim2} with byte strides s1, s2 and a {box0, 1, box2} box,
+ * 128-byte swizzle (box0 must be 16 doubles): the tile stores of k_alpha1024<.., TMA> */
+static int make_tmap_3d_sw128(nsb_tmap *out, const void *base, size_t dim0, size_t dim1, size_t dim2, size_t s1,
+                              size_t s2, int box0, int box2) {
+#ifdef NSB_EMULATE
+    out->base = (const double *)base;
+    out->dim0 = (long long)dim0; out->dim1 = (long long)dim1; out->dim2 = (long long)dim2;
+    out->stride1 = (long long)s1; out->stride2 = (long long)s2;
+    out->box0 = box0; out->box1 = 1; out->box2 = box2; out->swz = 1;
+    return 0;
+#else
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available");
+    const cuuint64_t gdim[3] = {(cuuint64_t)dim0, (cuuint64_t)dim1, (cuuint64_t)dim2};
+    const cuuint64_t gstr[2] = {(cuuint64_t)s1, (cuuint64_t)s2};
+    const cuuint32_t box[3] = {(cuuint32_t)box0, 1u, (cuuint32_t)box2};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = ((encode_fn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), gdim, gstr, box,
+                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
+    return 0;
+#endif
+}
+
 /* T / T' locations and the slab partition of the fused column kernel */
 static void fill_alpha_fast(nsb_ctx *c, AlphaFastArgs &fa, const cd *tp, int tp_pitch) {
     const NsbGeom &g = c->g;
@@ -706,20 +741,39 @@ static void fill_alpha_fast(nsb_ctx *c, AlphaFastArgs &fa, const cd *tp, int tp_
     fa.c1 = c->mg_c1;
 }
 
-static int launch_alpha1024(nsb_ctx *c, bool fwd, bool inv, const AlphaFastArgs &a) {
+static int launch_alpha1024(nsb_ctx *c, bool fwd, bool inv, const AlphaFastArgs &a_in) {
     const NsbGeom &g = c->g;
-    prof_pre(c, fwd ? PK_ALPHA_FWD : PK_ALPHA_INV);
-#define NSB_A1024(F, I, COLS)                                                                   \
-    {                                                                                           \
-        auto k = k_alpha1024<F, I, COLS>;                                                       \
-        const dim3 grid((a.c1 - a.c0 + COLS - 1) / COLS, g.Y2), block(COLS * 32);               \
-        if (ensure_smem(c, k, NSB_A1024_SMEM(COLS))) return -1;                                 \
-        NSB_LAUNCH(k, grid, block, NSB_A1024_SMEM(COLS), c->stream, g, a);                      \
+    AlphaFastArgs a = a_in;
+    const bool tma = c->alpha_tma && inv && g.Y2 > 1;
+    if (tma) {
+        a.tma_rl = g.Y1 / c->mg_world;
+        a.tma_br = a.tma_rl < 256 ? a.tma_rl : 256;
+        if (!c->tmA_ok) {
+            for (int p = 0; p < c->mg_world; ++p)
+                if (make_tmap_3d_sw128(&c->tmA.m[p], c->mg_T[p], (size_t)2 * g.PT, (size_t)g.Y2, (size_t)4 * a.tma_rl,
+                                       (size_t)g.PT * sizeof(cd), (size_t)g.Y2 * g.PT * sizeof(cd), 16, a.tma_br))
+                    return -1;
+            c->tmA_ok = 1;
+        }
     }
-    if (c->alpha_cols == 8) {
-        if (fwd && inv) NSB_A1024(true, true, 8) else if (fwd) NSB_A1024(true, false, 8) else NSB_A1024(false, true, 8)
+    prof_pre(c, fwd ? PK_ALPHA_FWD : PK_ALPHA_INV);
+#define NSB_A1024(F, I, COLS, T, SMEM)                                                          \
+    {                                                                                           \
+        auto k = k_alpha1024<F, I, COLS, T>;                                                    \
+        const dim3 grid((a.c1 - a.c0 + COLS - 1) / COLS, g.Y2), block(COLS * 32);               \
+        if (ensure_smem(c, k, SMEM)) return -1;                                                 \
+        NSB_LAUNCH(k, grid, block, SMEM, c->stream, g, a, c->tmA);                              \
+    }
+    if (tma) {
+        if (fwd) NSB_A1024(true, true, 8, true, NSB_A1024_SMEM_TMA) else NSB_A1024(false, true, 8, true, NSB_A1024_SMEM_TMA)
+    } else if (c->alpha_cols == 8) {
+        if (fwd && inv) NSB_A1024(true, true, 8, false, NSB_A1024_SMEM(8))
+        else if (fwd) NSB_A1024(true, false, 8, false, NSB_A1024_SMEM(8))
+        else NSB_A1024(false, true, 8, false, NSB_A1024_SMEM(8))
     } else {
-        if (fwd && inv) NSB_A1024(true, true, 4) else if (fwd) NSB_A1024(true, false, 4) else NSB_A1024(false, true, 4)
+        if (fwd && inv) NSB_A1024(true, true, 4, false, NSB_A1024_SMEM(4))
+        else if (fwd) NSB_A1024(true, false, 4, false, NSB_A1024_SMEM(4))
+        else NSB_A1024(false, true, 4, false, NSB_A1024_SMEM(4))
     }
 #undef NSB_A1024
     prof_post(c);
@@ -1529,7 +1583,7 @@ extern "C" int nsb_mgpu_setup(nsb_ctx *c, int rank, int world) {
     if (world == 1) {
         c->mg_cb = g.PT; c->mg_c0 = 0; c->mg_c1 = g.ncol; c->mg_rows = g.ny; c->mg_row_shift = 30;
     } else {
-        c->mg_cb = ((g.ncol + world - 1) / world + NSB_A1024_COLS - 1) / NSB_A1024_COLS * NSB_A1024_COLS;
+        c->mg_cb = ((g.ncol + world - 1) / world + 7) / 8 * 8; /* tiles of 4 or 8 columns never straddle two devices */
         c->mg_c0 = rank * c->mg_cb;
         c->mg_c1 = c->mg_c0 + c->mg_cb < g.ncol ? c->mg_c0 + c->mg_cb : g.ncol;
         if (c->mg_c1 < c->mg_c0) c->mg_c1 = c->mg_c0;
@@ -1543,6 +1597,7 @@ extern "C" int nsb_mgpu_setup(nsb_ctx *c, int rank, int world) {
     if (world == 1) { c->mg_T[0] = c->bufA; c->mg_Tp[0] = c->bufTp; c->mg_sc[0] = c->d_sc; }
     c->tmT_ok = 0;
     c->tmT8_ok = 0;
+    c->tmA_ok = 0;
     c->mg_ipc = 0;
     c->mg_epoch = 0;
     /* measured on 2 B200s: 128-byte peer stores (8 columns per CTA) beat 64-byte ones by ~25 % in the
@@ -1596,6 +1651,7 @@ extern "C" int nsb_mgpu_import(nsb_ctx *c, int peer, const unsigned char *handle
     c->mg_Tp[peer] = (cd *)ptrs[1];
     c->mg_sc[peer] = (NsbScalars *)ptrs[2];
     c->mg_ipc = 1;
+    c->tmA_ok = 0;
     return 0;
 #endif
 }
@@ -1622,6 +1678,7 @@ extern "C" int nsb_mgpu_link_local(nsb_ctx **cs, int n) {
             cs[i]->mg_sc[j] = cs[j]->d_sc;
         }
         cs[i]->mg_ipc = 0;
+        cs[i]->tmA_ok = 0;
     }
     return 0;
 }

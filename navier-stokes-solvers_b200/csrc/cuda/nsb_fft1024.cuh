@@ -139,4 +139,29 @@ __device__ __forceinline__ void nsb_fft1024_warp(cd (&x)[32], double *T, const c
     nsb_dft32<INV>(x);
 }
 
+/* warp FFT-1024 (nsb_fft1024.cuh) with an unpadded, XOR-swizzled 8 KB transpose buffer */
+template <bool INV>
+__device__ __forceinline__ void nsb_fft1024_warp_sw(cd (&x)[32], double *T, const cd *TW, int lane) {
+    nsb_dft32<INV>(x);
+#pragma unroll
+    for (int r = 1; r < 32; ++r) {
+        const cd tw = TW[r * 32 + lane];
+        x[r] = INV ? cmulc(x[r], tw) : cmul(x[r], tw);
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r) T[r * 32 + (lane ^ r)] = x[r].x;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 32; ++q) x[q].x = T[lane * 32 + (q ^ lane)];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; ++r) T[r * 32 + (lane ^ r)] = x[r].y;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 32; ++q) x[q].y = T[lane * 32 + (q ^ lane)];
+    __syncwarp();
+    nsb_dft32<INV>(x);
+}
+
+
 #endif

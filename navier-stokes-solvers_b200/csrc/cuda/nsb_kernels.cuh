@@ -31,6 +31,8 @@
 #include "nsb_fft.cuh"
 #include "nsb_fft1024.cuh"
 
+#define NSB_MAXP 8 /* devices of one NVSwitch domain */
+
 struct NsbGeom {
     int nx, ny, nkx;
     int Y1, Y2, X1, X2, X2h;
@@ -938,8 +940,6 @@ __global__ void __launch_bounds__(256) k_klayout_to_ref(NsbGeom g, const cd *K, 
     }
 }
 
-#define NSB_MAXP 8 /* devices of one NVSwitch domain */
-
 /*
  * Slab decomposition: this device owns retained columns [c0, c1) in spectral
  * space (K-layout state and T' are indexed by ic - c0) and the y rows
@@ -955,6 +955,7 @@ struct AlphaFastArgs {
     size_t out_fs;   /* field stride of T (own rows * out_pitch) */
     int out_pitch;
     int row_shift;   /* log2(rows per device) */
+    int tma_rl, tma_br; /* TMA stores: y1 rows per device, rows per box */
     int c0, c1;      /* own columns */
     const cd *Wsrc;  /* K-layout state feeding the inverse part when there is no forward part */
     NsbRk rk;        /* K-layout pointers */
@@ -963,6 +964,12 @@ struct AlphaFastArgs {
 /* modes per thread and round of the RK sweep: all their state loads are in flight together (the
  * transform registers are idle during the sweep, so there is room for 8 x 3 complex values) */
 #ifndef NSB_RK_BATCH
+/* tensor maps of the T buffer of every device (3-D: {2*PT doubles, Y2, 4 fields x own y1 rows},
+ * 128B swizzle) for the TMA tile stores of k_alpha1024<.., TMA = true> */
+struct NsbTmaps {
+    nsb_tmap m[NSB_MAXP];
+};
+
 #define NSB_RK_BATCH 4 /* measured: 8 (and telling the allocator x is dead during the sweep) is 20 % slower */
 #endif
 #ifndef NSB_TILE_UNROLL
@@ -972,6 +979,7 @@ struct AlphaFastArgs {
 #define NSB_UNROLL(n) NSB_PRAGMA_(unroll n)
 #define NSB_A1024_COLS 4 /* granularity of the column partition; kernels take 4 or 8 columns per CTA */
 #define NSB_A1024_SMEM(COLS) (1024 * 16 + 1024 * (COLS) * 16 + 32 * 16 + 1024 * 8)
+#define NSB_A1024_SMEM_TMA (NSB_A1024_SMEM(8) + 8 * 8192 + 1024)
 
 /* shared tile S[1024 rows][4 columns], 16-byte chunks XOR-swizzled so that row-wise
  * (cooperative, coalesced) and column-wise (per-warp FFT) accesses are both conflict free */
@@ -1023,12 +1031,15 @@ __device__ NSB_NOINLINE cd nsb_rk_update_call(const NsbRk *r, size_t idx, double
  *                y twiddle -> tile -> cooperative coalesced store to T[f]
  * Replaces k_alpha_fwd<RK> of stage s followed by k_alpha_inv<STEP> of stage s+1.
  */
-template <bool FWD, bool INV, int COLS>
-__global__ void __launch_bounds__(COLS * 32, 8 / COLS) k_alpha1024(NsbGeom g, AlphaFastArgs a) {
-    NSB_DYN_SMEM(cd, smem);
-    cd *TW = smem;
-    cd *S = smem + 1024;
-    cd *TB = S + 1024 * COLS; /* TB[m] = exp(-2 pi i (32 j2 m)/ny) */
+template <bool FWD, bool INV, int COLS, bool TMA>
+__global__ void __launch_bounds__(COLS * 32, 8 / COLS)
+    k_alpha1024(NsbGeom g, AlphaFastArgs a, const NSB_GRID_CONSTANT NsbTmaps tm) {
+    NSB_DYN_SMEM(cd, smem_raw);
+    /* TMA: the tile must start on a 1024-byte boundary so that nsb_sidx<8> IS the 128B swizzle */
+    cd *smem = TMA ? smem_raw + nsb_smem_align_pad(smem_raw, 1024) / sizeof(cd) : smem_raw;
+    cd *S = smem;
+    cd *TW = S + 1024 * COLS;
+    cd *TB = TW + 1024; /* TB[m] = exp(-2 pi i (32 j2 m)/ny) */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j2 = blockIdx.y, ic0 = a.c0 + blockIdx.x * COLS;
     const int ic = ic0 + warp;
@@ -1040,6 +1051,8 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS) k_alpha1024(NsbGeom g, Al
      * 1024-entry table in shared memory costs more in lost L1 than the extra complex multiply) */
     const cd ta = __ldg(&g.WY[(size_t)j2 * lane]);
     double *KY = reinterpret_cast<double *>(TB + 32); /* ky of this CTA's rows, indexed by j1 */
+    /* TMA: private 8 KB transpose buffer per warp, so the tile is not touched while its store drains */
+    double *TS = KY + 1024 + (size_t)(threadIdx.x >> 5) * 1024;
     for (int k = threadIdx.x; k < 1024; k += blockDim.x) KY[k] = __ldg(&g.kyK[(size_t)j2 * 1024 + k]);
     const double kxv = active ? __ldg(&g.kx[ic]) : 0.0;
     const size_t kbase = ((size_t)(ic - a.c0) * g.Y2 + j2) * 1024;
@@ -1099,7 +1112,16 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS) k_alpha1024(NsbGeom g, Al
                     x[m] = nsb_ik(kk, x[m]);
                 }
             }
-            nsb_fft1024_warp_col<true, COLS>(x, S, warp, TW, lane);
+            if (TMA) nsb_fft1024_warp_sw<true>(x, TS, TW, lane);
+            else nsb_fft1024_warp_col<true, COLS>(x, S, warp, TW, lane);
+        }
+        if (TMA && job >= 2) {
+            /* the tile store of the previous job ran behind this transform; it must have finished
+             * READING the tile before the tile is overwritten */
+            if (threadIdx.x == 0) nsb_tma_store_wait_read();
+            __syncthreads();
+        }
+        if (active) {
             if (job == 0) {
 #pragma unroll
                 for (int m = 0; m < 32; ++m) S[nsb_sidx<COLS>(lane + 32 * m, warp)] = cmk(x[m].x, -x[m].y);
@@ -1119,6 +1141,7 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS) k_alpha1024(NsbGeom g, Al
                 }
             }
         }
+        if (TMA && job >= 1) nsb_fence_proxy_async(); /* generic-proxy tile writes -> visible to the TMA store */
         __syncthreads();
         if (job == 0) {
             /* RK sweep: thread takes elements flat = tid + 32*COLS*i of the COLS x 1024 tile, four at a
@@ -1163,6 +1186,18 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS) k_alpha1024(NsbGeom g, Al
                     }
                 }
             }
+        } else if (TMA) {
+            /* one thread hands the whole tile to the TMA unit: 1024 / tma_br boxes of tma_br rows x 8
+             * columns, each to the device that owns those rows; no barrier, the next transform starts */
+            if (threadIdx.x == 0) {
+                for (int r0 = 0; r0 < 1024; r0 += a.tma_br) {
+                    const int owner = r0 / a.tma_rl;
+                    nsb_tma_3d_s2g(&tm.m[owner], S + (size_t)r0 * COLS, 2 * ic0, j2,
+                                   (job - 1) * a.tma_rl + (r0 - owner * a.tma_rl));
+                }
+                nsb_tma_store_commit();
+            }
+            continue;
         } else {
             if (ic0 + cc < a.c1) {
                 const size_t fo = (size_t)(job - 1) * a.out_fs + ic0 + cc;
@@ -1178,6 +1213,7 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS) k_alpha1024(NsbGeom g, Al
         }
         __syncthreads();
     }
+    if (TMA && INV && threadIdx.x == 0) nsb_tma_store_wait_read(); /* shared memory must outlive the last store */
 }
 
 #endif

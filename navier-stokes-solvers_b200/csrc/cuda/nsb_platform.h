@@ -140,6 +140,9 @@ struct nsb_tmap {
     long long dim0, dim1;     /* extent in doubles / rows */
     long long stride1;        /* row pitch in bytes */
     int box0, box1;
+    /* 3-D maps (nsb_tma_3d_s2g): extents / byte strides of dims 1, 2, box of dim 2, 128B swizzle */
+    long long dim2, stride2;
+    int box2, swz;
 };
 #define NSB_GRID_CONSTANT
 static inline void nsb_tma_2d_g2s(void *dst, const nsb_tmap *m, int c0, int c1, nsb_mbar_t *bar) {
@@ -156,6 +159,23 @@ static inline void nsb_tma_2d_g2s(void *dst, const nsb_tmap *m, int c0, int c1, 
     *bar -= bytes << 32;
     if ((*bar >> 32) == 0) *bar += 1;
 }
+/* shared -> global store of a {box0, 1, box2} box; smem rows are 128 bytes (box0 == 16 doubles) with
+ * the 16-byte chunk index XORed with (128-byte line index mod 8), i.e. TMA SWIZZLE_128B */
+static inline void nsb_tma_3d_s2g(const nsb_tmap *m, const void *src, int c0, int c1, int c2) {
+    const char *s = (const char *)src;
+    for (int r = 0; r < m->box2; ++r)
+        for (int e = 0; e < m->box0; ++e) {
+            const long long i2 = (long long)c2 + r, i1 = c1, i0 = (long long)c0 + e;
+            if (i2 < 0 || i2 >= m->dim2 || i1 < 0 || i1 >= m->dim1 || i0 < 0 || i0 >= m->dim0) continue;
+            const size_t line = ((size_t)(s + (size_t)r * m->box0 * 8) >> 7) & 7;
+            const int chunk = e >> 1;
+            const int pch = m->swz ? (chunk ^ (int)line) : chunk;
+            const double v = *(const double *)(s + (size_t)r * m->box0 * 8 + (size_t)pch * 16 + (e & 1) * 8);
+            *(double *)((char *)m->base + i2 * m->stride2 + i1 * m->stride1 + i0 * 8) = v;
+        }
+}
+static inline void nsb_tma_store_commit() {}
+static inline void nsb_tma_store_wait_read() {}
 #else
 #include <cuda.h>
 typedef CUtensorMap nsb_tmap;
@@ -166,6 +186,17 @@ __device__ __forceinline__ void nsb_tma_2d_g2s(void *dst, const nsb_tmap *map, i
             nsb_smem_addr(dst)),
         "l"(map), "r"(c0), "r"(c1), "r"(nsb_smem_addr(bar))
         : "memory");
+}
+/* shared -> global tensor store (SASS UTMASTG), tracked by bulk async-groups: commit after
+ * issuing, wait_read before the shared-memory source is overwritten */
+__device__ __forceinline__ void nsb_tma_3d_s2g(const nsb_tmap *map, const void *src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(nsb_smem_addr(src))
+                 : "memory");
+}
+__device__ __forceinline__ void nsb_tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void nsb_tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 #endif
 
