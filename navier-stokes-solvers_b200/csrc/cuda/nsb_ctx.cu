@@ -744,15 +744,20 @@ static void fill_alpha_fast(nsb_ctx *c, AlphaFastArgs &fa, const cd *tp, int tp_
 static int launch_alpha1024(nsb_ctx *c, bool fwd, bool inv, const AlphaFastArgs &a_in) {
     const NsbGeom &g = c->g;
     AlphaFastArgs a = a_in;
-    const bool tma = c->alpha_tma && inv && g.Y2 > 1;
+    const bool tma = c->alpha_tma && g.Y2 > 1 &&
+                     (inv || (fwd && c->bufTp && a.in == c->bufTp && a.in_pitch == c->mg_cb));
     if (tma) {
         a.tma_rl = g.Y1 / c->mg_world;
+        a.tma_in = (fwd && c->bufTp && a.in == c->bufTp && a.in_pitch == c->mg_cb) ? 1 : 0;
         a.tma_br = a.tma_rl < 256 ? a.tma_rl : 256;
         if (!c->tmA_ok) {
             for (int p = 0; p < c->mg_world; ++p)
                 if (make_tmap_3d_sw128(&c->tmA.m[p], c->mg_T[p], (size_t)2 * g.PT, (size_t)g.Y2, (size_t)4 * a.tma_rl,
                                        (size_t)g.PT * sizeof(cd), (size_t)g.Y2 * g.PT * sizeof(cd), 16, a.tma_br))
                     return -1;
+            if (c->bufTp && make_tmap_3d_sw128(&c->tmA.tp, c->bufTp, (size_t)2 * c->mg_cb, (size_t)g.Y2, (size_t)g.Y1,
+                                               (size_t)c->mg_cb * sizeof(cd), (size_t)g.Y2 * c->mg_cb * sizeof(cd), 16, 256))
+                return -1;
             c->tmA_ok = 1;
         }
     }
@@ -765,7 +770,9 @@ static int launch_alpha1024(nsb_ctx *c, bool fwd, bool inv, const AlphaFastArgs 
         NSB_LAUNCH(k, grid, block, SMEM, c->stream, g, a, c->tmA);                              \
     }
     if (tma) {
-        if (fwd) NSB_A1024(true, true, 8, true, NSB_A1024_SMEM_TMA) else NSB_A1024(false, true, 8, true, NSB_A1024_SMEM_TMA)
+        if (fwd && inv) NSB_A1024(true, true, 8, true, NSB_A1024_SMEM_TMA)
+        else if (fwd) NSB_A1024(true, false, 8, true, NSB_A1024_SMEM_TMA)
+        else NSB_A1024(false, true, 8, true, NSB_A1024_SMEM_TMA)
     } else if (c->alpha_cols == 8) {
         if (fwd && inv) NSB_A1024(true, true, 8, false, NSB_A1024_SMEM(8))
         else if (fwd) NSB_A1024(true, false, 8, false, NSB_A1024_SMEM(8))

@@ -956,6 +956,7 @@ struct AlphaFastArgs {
     int out_pitch;
     int row_shift;   /* log2(rows per device) */
     int tma_rl, tma_br; /* TMA stores: y1 rows per device, rows per box */
+    int tma_in;      /* the forward tile comes from the T' exchange buffer the tensor map tm.tp describes */
     int c0, c1;      /* own columns */
     const cd *Wsrc;  /* K-layout state feeding the inverse part when there is no forward part */
     NsbRk rk;        /* K-layout pointers */
@@ -968,6 +969,7 @@ struct AlphaFastArgs {
  * 128B swizzle) for the TMA tile stores of k_alpha1024<.., TMA = true> */
 struct NsbTmaps {
     nsb_tmap m[NSB_MAXP];
+    nsb_tmap tp; /* the local T' buffer: {2*cb doubles, Y2, Y1}, for the TMA load of the forward tile */
 };
 
 #define NSB_RK_BATCH 4 /* measured: 8 (and telling the allocator x is dead during the sweep) is 20 % slower */
@@ -979,7 +981,7 @@ struct NsbTmaps {
 #define NSB_UNROLL(n) NSB_PRAGMA_(unroll n)
 #define NSB_A1024_COLS 4 /* granularity of the column partition; kernels take 4 or 8 columns per CTA */
 #define NSB_A1024_SMEM(COLS) (1024 * 16 + 1024 * (COLS) * 16 + 32 * 16 + 1024 * 8)
-#define NSB_A1024_SMEM_TMA (NSB_A1024_SMEM(8) + 8 * 8192 + 1024)
+#define NSB_A1024_SMEM_TMA (NSB_A1024_SMEM(8) + 8 * 8192 + 16 + 1024)
 
 /* shared tile S[1024 rows][4 columns], 16-byte chunks XOR-swizzled so that row-wise
  * (cooperative, coalesced) and column-wise (per-warp FFT) accesses are both conflict free */
@@ -1057,7 +1059,18 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
     const double kxv = active ? __ldg(&g.kx[ic]) : 0.0;
     const size_t kbase = ((size_t)(ic - a.c0) * g.Y2 + j2) * 1024;
     const cd *Wre = FWD ? a.rk.Wst : a.Wsrc; /* state the inverse fields derive from */
-    if (FWD) {
+    nsb_mbar_t *tbar = reinterpret_cast<nsb_mbar_t *>(KY + 1024 + 8 * 1024); /* TMA only: behind the scratch */
+    if (FWD && TMA && a.tma_in) {
+        /* the whole T' tile (1024 rows x 8 columns) in four tensor loads, in flight while the
+         * twiddle / ky tables above are filled by the other threads */
+        if (threadIdx.x == 0) {
+            nsb_mbar_init(tbar, 1);
+            nsb_fence_proxy_async();
+            nsb_mbar_expect_tx(tbar, 1024u * COLS * 16u);
+            for (int r0 = 0; r0 < 1024; r0 += 256)
+                nsb_tma_3d_g2s(S + (size_t)r0 * COLS, &tm.tp, 2 * (ic0 - a.c0), j2, r0, tbar);
+        }
+    } else if (FWD) {
         const bool colok = ic0 + cc < a.c1;
         NSB_UNROLL(NSB_TILE_UNROLL)
         for (int i = 0; i < 32; ++i) {
@@ -1068,6 +1081,7 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
         }
     }
     __syncthreads();
+    if (FWD && TMA && a.tma_in) nsb_mbar_wait(tbar, 0u);
     cd x[32];
     bool prefetched = false;
     /* rows of this lane that survive the 2/3 mask, one bit per register index (same for every job) */

@@ -174,6 +174,24 @@ static inline void nsb_tma_3d_s2g(const nsb_tmap *m, const void *src, int c0, in
             *(double *)((char *)m->base + i2 * m->stride2 + i1 * m->stride1 + i0 * 8) = v;
         }
 }
+/* global -> shared load of a {box0, 1, box2} box, same swizzle convention */
+static inline void nsb_tma_3d_g2s(void *dst, const nsb_tmap *m, int c0, int c1, int c2, nsb_mbar_t *bar) {
+    char *d = (char *)dst;
+    for (int r = 0; r < m->box2; ++r)
+        for (int e = 0; e < m->box0; ++e) {
+            const long long i2 = (long long)c2 + r, i1 = c1, i0 = (long long)c0 + e;
+            double v = 0.0;
+            if (i2 >= 0 && i2 < m->dim2 && i1 >= 0 && i1 < m->dim1 && i0 >= 0 && i0 < m->dim0)
+                v = *(const double *)((const char *)m->base + i2 * m->stride2 + i1 * m->stride1 + i0 * 8);
+            const size_t line = ((size_t)(d + (size_t)r * m->box0 * 8) >> 7) & 7;
+            const int chunk = e >> 1;
+            const int pch = m->swz ? (chunk ^ (int)line) : chunk;
+            *(double *)(d + (size_t)r * m->box0 * 8 + (size_t)pch * 16 + (e & 1) * 8) = v;
+        }
+    const unsigned long long bytes = (unsigned long long)m->box0 * m->box2 * 8ull;
+    *bar -= bytes << 32;
+    if ((*bar >> 32) == 0) *bar += 1;
+}
 static inline void nsb_tma_store_commit() {}
 static inline void nsb_tma_store_wait_read() {}
 #else
@@ -185,6 +203,13 @@ __device__ __forceinline__ void nsb_tma_2d_g2s(void *dst, const nsb_tmap *map, i
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
             nsb_smem_addr(dst)),
         "l"(map), "r"(c0), "r"(c1), "r"(nsb_smem_addr(bar))
+        : "memory");
+}
+__device__ __forceinline__ void nsb_tma_3d_g2s(void *dst, const nsb_tmap *map, int c0, int c1, int c2, nsb_mbar_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            nsb_smem_addr(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(nsb_smem_addr(bar))
         : "memory");
 }
 /* shared -> global tensor store (SASS UTMASTG), tracked by bulk async-groups: commit after
