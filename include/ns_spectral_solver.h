@@ -150,6 +150,9 @@ typedef enum { NS_SYNC_EAGER = 0, NS_SYNC_LAZY = 1 } NSSyncPolicy;
 /* CUDA device used by the next ns_spectral_initialize_fft_plans (default 0 or
  * $NS_SPECTRAL_DEVICE). Returns 0, or -1 if the context already exists. */
 int ns_spectral_backend_select_device(NSSpectralData *data, int device);
+/* slab-decompose over n_gpus devices driven by this process (after initialize_fft_plans);
+ * ns_spectral_run_steps then advances the one grid on all of them. 0 / -1 + ns_spectral_last_error() */
+int ns_spectral_backend_init(NSSpectralData *data, int n_gpus);
 void ns_spectral_set_sync_policy(NSSpectralData *data, NSSyncPolicy policy);
 NSSyncPolicy ns_spectral_get_sync_policy(const NSSpectralData *data);
 /* device -> host: derived fields are recomputed on the device from omega_hat first */

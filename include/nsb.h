@@ -172,6 +172,10 @@ int nsb_mgpu_export(nsb_ctx *c, unsigned char *handles);
 int nsb_mgpu_import(nsb_ctx *c, int peer, const unsigned char *handles);
 int nsb_mgpu_link_local(nsb_ctx **ctxs, int n);
 int nsb_mgpu_group_step(nsb_ctx **ctxs, int n, double dt);
+/* single-process group: bring ctxs[0]'s reference-layout OMEGA_HAT / SFD_HAT up to date from all
+ * devices (gather) or publish it to all devices after the host changed it (scatter) */
+int nsb_mgpu_group_gather(nsb_ctx **ctxs, int n);
+int nsb_mgpu_group_scatter(nsb_ctx **ctxs, int n);
 
 /* number of kernels this library has launched on this context */
 long long nsb_launch_count(nsb_ctx *c);

@@ -96,6 +96,8 @@ def load_nsb(path=None):
         "nsb_mgpu_import": [C.c_void_p, C.c_int, C.c_char_p],
         "nsb_mgpu_link_local": [C.POINTER(C.c_void_p), C.c_int],
         "nsb_mgpu_group_step": [C.POINTER(C.c_void_p), C.c_int, C.c_double],
+        "nsb_mgpu_group_gather": [C.POINTER(C.c_void_p), C.c_int],
+        "nsb_mgpu_group_scatter": [C.POINTER(C.c_void_p), C.c_int],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)

@@ -1717,3 +1717,63 @@ extern "C" int nsb_mgpu_group_step(nsb_ctx **cs, int n, double dt) {
     }
     return 0;
 }
+
+/* Single-process group: make cs[0]'s reference-layout OMEGA_HAT (and SFD_HAT) complete and current
+ * from the own-column blocks of all devices, so that every single-device entry point
+ * (diagnostics, transforms, download) can run on cs[0]. The other devices keep their own
+ * columns current, so stepping can continue without a scatter. Synchronous. */
+extern "C" int nsb_mgpu_group_gather(nsb_ctx **cs, int n) {
+    if (!cs || n < 1 || n > NSB_MAXP) return fail("nsb_mgpu_group_gather: bad arguments");
+    for (int r = 0; r < n; ++r) {
+        if (!cs[r]) return fail("nsb_mgpu_group_gather: null context");
+        CK(cudaSetDevice(cs[r]->device));
+        if (sync_ref(cs[r])) return -1;
+        CK(cudaStreamSynchronize(cs[r]->stream));
+    }
+    const int fields[2] = {NSB_OMEGA_HAT, NSB_SFD_HAT};
+    for (int fi = 0; fi < 2; ++fi) {
+        if (fi == 1 && !cs[0]->hv.sfd) break;
+        void *dst0;
+        CK(cudaSetDevice(cs[0]->device));
+        if (get_field(cs[0], fields[fi], &dst0)) return -1;
+        for (int r = 1; r < n; ++r) {
+            void *src;
+            CK(cudaSetDevice(cs[r]->device));
+            if (get_field(cs[r], fields[fi], &src)) return -1;
+            const int w = cs[r]->mg_c1 - cs[r]->mg_c0;
+            if (w <= 0) continue;
+            const size_t pitch = (size_t)cs[r]->g.nkx * sizeof(cd);
+            CK(cudaMemcpy2DAsync((cd *)dst0 + cs[r]->mg_c0, pitch, (const cd *)src + cs[r]->mg_c0, pitch,
+                                 (size_t)w * sizeof(cd), (size_t)cs[r]->g.ny, cudaMemcpyDefault, cs[r]->stream));
+            CK(cudaStreamSynchronize(cs[r]->stream));
+        }
+    }
+    return 0;
+}
+
+/* Single-process group: cs[0]'s reference-layout OMEGA_HAT (and SFD_HAT) was written by the host
+ * or by a single-device entry point; copy it to every other device. Synchronous. */
+extern "C" int nsb_mgpu_group_scatter(nsb_ctx **cs, int n) {
+    if (!cs || n < 1 || n > NSB_MAXP) return fail("nsb_mgpu_group_scatter: bad arguments");
+    CK(cudaSetDevice(cs[0]->device));
+    if (sync_ref(cs[0])) return -1;
+    CK(cudaStreamSynchronize(cs[0]->stream));
+    const int fields[2] = {NSB_OMEGA_HAT, NSB_SFD_HAT};
+    for (int r = 1; r < n; ++r) {
+        CK(cudaSetDevice(cs[r]->device));
+        if (sync_ref(cs[r])) return -1;
+        for (int fi = 0; fi < 2; ++fi) {
+            if (fi == 1 && !cs[0]->hv.sfd) break;
+            void *src, *dst;
+            CK(cudaSetDevice(cs[0]->device));
+            if (get_field(cs[0], fields[fi], &src)) return -1;
+            CK(cudaSetDevice(cs[r]->device));
+            if (get_field(cs[r], fields[fi], &dst)) return -1;
+            CK(cudaMemcpyAsync(dst, src, cs[0]->M * sizeof(cd), cudaMemcpyDefault, cs[r]->stream));
+        }
+        CK(cudaStreamSynchronize(cs[r]->stream));
+        cs[r]->k_truth = 0;
+        cs[r]->masked_nonzero = cs[0]->masked_nonzero;
+    }
+    return 0;
+}

@@ -19,7 +19,7 @@
  *   spectral.sfd.strength [0 = off]  spectral.sfd.timescale [1]
  *   init.type taylor_green|random_phase [taylor_green]  init.seed [7]  init.k0 [8]
  *   init.max_omega [5]   output.interval [50, 0 = none]  output.prefix [spectral_solution]
- *   backend.device [0]
+ *   backend.device [0]   backend.gpus [1] (slab decomposition over devices device..device+gpus-1)
  */
 #include "ns_config.h"
 #include "ns_spectral_solver.h"
@@ -74,6 +74,7 @@ static int load_config(int argc, char **argv, NSConfig *cfg) {
         {"init.type", NS_CONFIG_VALUE_STRING, 0, 0, 0, 0, 0, init_ok, 2},
         {"output.interval", NS_CONFIG_VALUE_INT, 0, 0, 0, 1, 0, NULL, 0},
         {"backend.device", NS_CONFIG_VALUE_INT, 0, 0, 0, 1, 0, NULL, 0},
+        {"backend.gpus", NS_CONFIG_VALUE_INT, 0, 1, 8, 1, 1, NULL, 0},
     };
     if (ns_config_validate(cfg, schema, sizeof schema / sizeof schema[0], err, sizeof err) != 0) {
         fprintf(stderr, "configuration error: %s\n", err);
@@ -124,6 +125,12 @@ int main(int argc, char *argv[]) {
     ns_spectral_initialize_fft_plans(data);
     if (!data->forward_plan) {
         fprintf(stderr, "no usable CUDA device: %s\n", ns_spectral_last_error());
+        ns_spectral_free(data);
+        return 3;
+    }
+    const int gpus = ns_config_get_int(&cfg, "backend.gpus", 1);
+    if (gpus > 1 && ns_spectral_backend_init(data, gpus) != 0) {
+        fprintf(stderr, "backend.gpus = %d: %s\n", gpus, ns_spectral_last_error());
         ns_spectral_free(data);
         return 3;
     }

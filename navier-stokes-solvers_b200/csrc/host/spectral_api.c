@@ -17,6 +17,11 @@ typedef struct {
     nsb_ctx *ctx;
     int device;
     NSSyncPolicy policy;
+    /* ns_spectral_backend_init: slab decomposition over several devices driven by this process.
+     * group[0] == ctx. `gathered`: ctx's reference-layout omega_hat is complete (single-device entry
+     * points may run on it); `dirty`: it may have been changed since the other devices last saw it. */
+    nsb_ctx *group[8];
+    int ngpus, gathered, dirty;
     /* forcing fast path: ascending active-index list of the last NSForcingState seen */
     const NSForcingState *forcing_owner;
     int *forcing_idx;
@@ -44,18 +49,29 @@ static void die(const char *where, const char *why) {
     abort();
 }
 
-static nsb_ctx *ctx_of(NSSpectralData *d, const char *where) {
-    Backend *b = backend_of(d);
-    if (!d || !b) die(where, "NULL solver data");
-    if (!b->ctx) die(where, "no device context: call ns_spectral_initialize_fft_plans() on a machine with a "
-                            "CUDA device first (there is no CPU fallback)");
-    return b->ctx;
-}
-
 #define NSB_OK(call, where)                               \
     do {                                                  \
         if ((call) != 0) die(where, nsb_last_error());    \
     } while (0)
+
+/* the primary context for a single-device entry point; in a device group the own-column blocks
+ * of all devices are gathered into it first. `modifies`: the call may change omega_hat there. */
+static nsb_ctx *ctx_get(NSSpectralData *d, const char *where, int modifies) {
+    Backend *b = backend_of(d);
+    if (!d || !b) die(where, "NULL solver data");
+    if (!b->ctx) die(where, "no device context: call ns_spectral_initialize_fft_plans() on a machine with a "
+                            "CUDA device first (there is no CPU fallback)");
+    if (b->ngpus > 1) {
+        if (!b->gathered) {
+            NSB_OK(nsb_mgpu_group_gather(b->group, b->ngpus), where);
+            b->gathered = 1;
+        }
+        if (modifies) b->dirty = 1;
+    }
+    return b->ctx;
+}
+static nsb_ctx *ctx_of(NSSpectralData *d, const char *where) { return ctx_get(d, where, 1); }
+static nsb_ctx *ctx_ro(NSSpectralData *d, const char *where) { return ctx_get(d, where, 0); }
 
 static size_t n_phys(const NSSpectralData *d) { return (size_t)d->nx * (size_t)d->ny; }
 static size_t n_spec(const NSSpectralData *d) { return (size_t)d->nkx * (size_t)d->nky; }
@@ -108,6 +124,8 @@ void ns_spectral_free(NSSpectralData *d) {
     if (!d) return;
     Backend *b = backend_of(d);
     if (b) {
+        for (int r = 1; r < b->ngpus; ++r)
+            if (b->group[r]) nsb_ctx_destroy(b->group[r]);
         if (b->ctx) nsb_ctx_destroy(b->ctx);
         free(b->forcing_idx);
         free(b->forcing_box);
@@ -160,6 +178,7 @@ static void push_hyperviscosity(NSSpectralData *d) {
     p.sfd_strength = h->sfd_strength;
     p.sfd_timescale = h->sfd_timescale;
     NSB_OK(nsb_set_hyperviscosity(b->ctx, &p), "hyperviscosity");
+    for (int r = 1; r < b->ngpus; ++r) NSB_OK(nsb_set_hyperviscosity(b->group[r], &p), "hyperviscosity");
 }
 
 /* spectral_initialization.c:57-69: "plan creation" = device context creation */
@@ -187,7 +206,7 @@ static void upload(NSSpectralData *d, int field, const void *host, const char *w
     NSB_OK(nsb_upload(ctx_of(d, where), field, host), where);
 }
 static void download(NSSpectralData *d, int field, void *host, const char *where) {
-    NSB_OK(nsb_download(ctx_of(d, where), field, host), where);
+    NSB_OK(nsb_download(ctx_ro(d, where), field, host), where);
 }
 
 /* device: psi_hat,u_hat,v_hat,u,v,omega from omega_hat; host arrays refreshed */
@@ -471,16 +490,35 @@ int ns_spectral_run_steps(NSSpectralData *d, int n, NSForcingState *fs) {
     }
     NSB_OK(nsb_set_time(c, d->t), W);
     if (fs && bind_forcing(d, fs) != 0) return -1;
-    if (!fs) NSB_OK(nsb_set_forcing(c, 0, 0, NULL), W);
+    const int group = b->ngpus > 1;
+    if (group) {
+        if (fs && fs->config.type == NS_FORCING_COLORED_NOISE) {
+            set_error("%s: coloured forcing needs the CFL step on the host before every step; not supported on a "
+                      "device group", W);
+            return -1;
+        }
+        /* publish what the single-device entry points did to omega_hat since the last group step */
+        if (b->dirty) NSB_OK(nsb_mgpu_group_scatter(b->group, b->ngpus), W);
+        b->dirty = 0;
+        for (int r = 1; r < b->ngpus; ++r) NSB_OK(nsb_set_time(b->group[r], d->t), W);
+    }
+    for (int r = 0; r < (group ? b->ngpus : 1); ++r)
+        if (!fs) NSB_OK(nsb_set_forcing(group ? b->group[r] : c, 0, 0, NULL), W);
     for (int s = 0; s < n; ++s) {
         double dt = 0.0; /* 0 = CFL step computed on the device inside the step */
         if (fs) {
             /* coloured noise needs dt before the stream is consumed (forcing.c:138-147) */
             if (fs->config.type == NS_FORCING_COLORED_NOISE) NSB_OK(nsb_cfl_timestep(c, &dt), W);
             ns_forcing_generate_box(fs, dt, b->forcing_idx, b->ib, b->jb, b->forcing_box);
-            NSB_OK(nsb_set_forcing(c, b->ib, b->jb, (const double *)b->forcing_box), W);
+            for (int r = 0; r < (group ? b->ngpus : 1); ++r)
+                NSB_OK(nsb_set_forcing(group ? b->group[r] : c, b->ib, b->jb, (const double *)b->forcing_box), W);
         }
-        NSB_OK(nsb_rk4_step(c, dt), W);
+        if (group) {
+            NSB_OK(nsb_mgpu_group_step(b->group, b->ngpus, dt), W);
+            b->gathered = 0;
+        } else {
+            NSB_OK(nsb_rk4_step(c, dt), W);
+        }
     }
     int steps = 0;
     NSB_OK(nsb_get_state(c, &d->dt, &d->t, &steps), W);
@@ -495,7 +533,7 @@ int ns_spectral_run_steps(NSSpectralData *d, int n, NSForcingState *fs) {
 /* ------------------------------------------------------------- diagnostics */
 
 static void sums(NSSpectralData *d, double out[4], const char *where) {
-    nsb_ctx *c = ctx_of(d, where);
+    nsb_ctx *c = ctx_ro(d, where);
     if (lazy(d)) {
         NSB_OK(nsb_diagnostics(c, out), where);
     } else {
@@ -524,7 +562,7 @@ static void lazy_fetch_spectra(NSSpectralData *d, int with_velocity, const char 
     if (!lazy(d)) return;
     download(d, NSB_OMEGA_HAT, d->omega_hat, where);
     if (with_velocity) {
-        NSB_OK(nsb_velocity_from_vorticity(ctx_of(d, where)), where);
+        NSB_OK(nsb_velocity_from_vorticity(ctx_ro(d, where)), where);
         download(d, NSB_U_HAT, d->u_hat, where);
         download(d, NSB_V_HAT, d->v_hat, where);
     }
@@ -711,7 +749,7 @@ void ns_spectral_hyperviscosity_post_step(NSSpectralData *d, const fftw_complex 
 /* spectral_output.c:4-27 */
 void ns_spectral_output_solution(NSSpectralData *d, const char *filename) {
     static const char *W = "ns_spectral_output_solution";
-    nsb_ctx *c = ctx_of(d, W);
+    nsb_ctx *c = ctx_ro(d, W);
     FILE *fp = fopen(filename, "w");
     if (!fp) return;
     if (lazy(d)) {
@@ -747,6 +785,54 @@ int ns_spectral_backend_select_device(NSSpectralData *d, int device) {
     return 0;
 }
 
+/* slab-decompose this solver over n_gpus devices driven by this process (devices
+ * device .. device+n_gpus-1; NS_SPECTRAL_GROUP_SAME_DEVICE=1 keeps them all on `device`, for
+ * machines with fewer GPUs). Call after ns_spectral_initialize_fft_plans. ns_spectral_run_steps
+ * then advances the one grid on all devices; every other entry point gathers the state into the
+ * first device and runs there. */
+int ns_spectral_backend_init(NSSpectralData *d, int n_gpus) {
+    static const char *W = "ns_spectral_backend_init";
+    Backend *b = backend_of(d);
+    if (!b || !b->ctx) { set_error("%s: call ns_spectral_initialize_fft_plans first", W); return -1; }
+    if (b->ngpus > 1) { set_error("%s: already initialised", W); return -1; }
+    if (n_gpus <= 1) return 0;
+    if (n_gpus > 8) { set_error("%s: at most 8 devices", W); return -1; }
+    const char *same = getenv("NS_SPECTRAL_GROUP_SAME_DEVICE");
+    const int same_dev = same && atoi(same);
+    b->group[0] = b->ctx;
+    for (int r = 1; r < n_gpus; ++r) {
+        nsb_params p;
+        memset(&p, 0, sizeof p);
+        p.nx = d->nx; p.ny = d->ny; p.Lx = d->Lx; p.Ly = d->Ly; p.Re = d->Re;
+        p.cfl_factor = d->cfl_factor;
+        p.device = same_dev ? b->device : b->device + r;
+        if (nsb_ctx_create(&p, &b->group[r]) != 0) {
+            set_error("%s: %s", W, nsb_last_error());
+            for (int q = 1; q < r; ++q) nsb_ctx_destroy(b->group[q]);
+            return -1;
+        }
+    }
+    for (int r = 0; r < n_gpus; ++r) {
+        if (nsb_mgpu_setup(b->group[r], r, n_gpus) != 0) {
+            set_error("%s: %s", W, nsb_last_error());
+            for (int q = 1; q < n_gpus; ++q) nsb_ctx_destroy(b->group[q]);
+            nsb_mgpu_setup(b->ctx, 0, 1);
+            return -1;
+        }
+    }
+    if (nsb_mgpu_link_local(b->group, n_gpus) != 0) {
+        set_error("%s: %s", W, nsb_last_error());
+        for (int q = 1; q < n_gpus; ++q) nsb_ctx_destroy(b->group[q]);
+        nsb_mgpu_setup(b->ctx, 0, 1);
+        return -1;
+    }
+    b->ngpus = n_gpus;
+    b->gathered = 1; /* the first device holds everything so far */
+    b->dirty = 1;
+    push_hyperviscosity(d);
+    return 0;
+}
+
 void ns_spectral_set_sync_policy(NSSpectralData *d, NSSyncPolicy policy) {
     Backend *b = backend_of(d);
     if (!b) return;
@@ -768,7 +854,7 @@ NSSyncPolicy ns_spectral_get_sync_policy(const NSSpectralData *d) {
 
 int ns_spectral_sync_to_host(NSSpectralData *d, unsigned mask) {
     static const char *W = "ns_spectral_sync_to_host";
-    nsb_ctx *c = ctx_of(d, W);
+    nsb_ctx *c = ctx_ro(d, W);
     if (mask & NS_FIELD_OMEGA_HAT) download(d, NSB_OMEGA_HAT, d->omega_hat, W);
     if (mask & NS_FIELD_SFD_HAT) {
         const NSSpectralHyperviscosityConfig *h = &d->hyperviscosity;

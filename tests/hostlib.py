@@ -48,7 +48,7 @@ SPECTRAL_SYMBOLS = [
     "ns_spectral_backend_select_device", "ns_spectral_set_sync_policy", "ns_spectral_get_sync_policy",
     "ns_spectral_sync_to_host", "ns_spectral_sync_to_device", "ns_spectral_advance_rk4_forced",
     "ns_spectral_run_steps", "ns_spectral_initialize_random_phase", "ns_spectral_last_error",
-    "ns_spectral_backend_context",
+    "ns_spectral_backend_context", "ns_spectral_backend_init",
 ]
 FORCING_SYMBOLS = ["ns_forcing_config_default", "ns_forcing_state_init", "ns_forcing_state_free",
                    "ns_forcing_generate", "ns_forcing_box_extent", "ns_forcing_active_indices",
@@ -66,7 +66,7 @@ NSB_SYMBOLS = [
     "nsb_get_dt_history", "nsb_get_plan", "nsb_stream", "nsb_timer_start", "nsb_timer_stop", "nsb_profile_begin", "nsb_profile_end",
     "nsb_launch_count",
     "nsb_mgpu_setup", "nsb_mgpu_partition", "nsb_mgpu_export", "nsb_mgpu_import", "nsb_mgpu_link_local",
-    "nsb_mgpu_group_step",
+    "nsb_mgpu_group_step", "nsb_mgpu_group_gather", "nsb_mgpu_group_scatter",
 ]
 
 
@@ -113,6 +113,7 @@ def load(path):
     lib.ns_spectral_run_steps.argtypes = [SP, C.c_int, C.POINTER(orc.ForcingState)]
     lib.ns_spectral_initialize_random_phase.argtypes = [SP, C.c_ulonglong, C.c_double, C.c_double]
     lib.ns_spectral_last_error.restype = C.c_char_p
+    lib.ns_spectral_backend_init.argtypes = [SP, C.c_int]
     lib.ns_forcing_config_default.restype = None
     lib.ns_forcing_config_default.argtypes = [C.POINTER(orc.ForcingConfig)]
     lib.ns_forcing_state_init.argtypes = [C.POINTER(orc.ForcingState), C.POINTER(orc.ForcingConfig), c_double_p,

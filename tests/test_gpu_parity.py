@@ -194,3 +194,48 @@ def test_free_running_fast_path_2048(nsb, cuda_lib, oracles):
     enstrophy within 1e-9 relative (observed ~1e-13)."""
     pc.check_free_running(nsb, cuda_lib, oracles, best_oracle_kind(oracles), 2048, 2048, 200, every=20, hv=HV,
                           forcing=dict(kind="white"), Re=1e4)
+
+
+def _host_run(host, n, gpus, steps_a=2, steps_b=2):
+    """forced run through the reference-facing entry points: steps, diagnostics (gather), steps"""
+    import ctypes as C
+    import hostlib
+    import orc
+    s = hostlib.Solver(host, n, n, Re=1e4)
+    if gpus > 1:
+        assert host.ns_spectral_backend_init(s.sp, gpus) == 0, host.ns_spectral_last_error()
+    s.arr("omega_hat")[...] = _turbulence_block(n, 33)
+    h = orc.Hyperviscosity()
+    host.ns_spectral_hyperviscosity_default(C.byref(h))
+    h.enabled, h.coefficient, h.order, h.cutoff_ratio = 1, 5.0, 4, 0.3
+    host.ns_spectral_hyperviscosity_set(s.sp, C.byref(h))
+    cfg = orc.ForcingConfig()
+    host.ns_forcing_config_default(C.byref(cfg))
+    cfg.kmin, cfg.kmax, cfg.energy_target, cfg.seed, cfg.type = 0.5, 4.0, 1.25, 42, 0
+    fs = orc.ForcingState()
+    assert host.ns_forcing_state_init(C.byref(fs), C.byref(cfg), s.s.k2, s.s.nkx, s.s.nky) == 0
+    host.ns_spectral_set_sync_policy(s.sp, 1)
+    assert host.ns_spectral_run_steps(s.sp, steps_a, C.byref(fs)) == 0
+    e1 = host.ns_spectral_compute_energy(s.sp)          # gathers into the first device
+    assert host.ns_spectral_run_steps(s.sp, steps_b, C.byref(fs)) == 0
+    host.ns_spectral_sync_to_host(s.sp, 0xFFFFFFFF)
+    out = (np.array(s.arr("omega_hat")), e1, host.ns_spectral_compute_enstrophy(s.sp), s.s.t, s.s.dt)
+    host.ns_forcing_state_free(C.byref(fs))
+    s.close()
+    return out
+
+
+def test_host_backend_init_device_group(monkeypatch):
+    """ns_spectral_backend_init(data, n): the reference-facing entry points on a slab-decomposed
+    device group (here n logical devices on GPU 0) reproduce the single-device run bit for bit,
+    with diagnostics (gather) between two batches of steps."""
+    import hostlib
+    monkeypatch.setenv("NS_SPECTRAL_GROUP_SAME_DEVICE", "1")
+    host = hostlib.load(hostlib.PRODUCT)
+    ref = _host_run(host, 2048, 1)
+    for gpus in (2, 4):
+        got = _host_run(host, 2048, gpus)
+        assert np.array_equal(got[0], ref[0])
+        assert got[3:] == ref[3:]                      # t, dt: bit-identical
+        for a, b in zip(got[1:3], ref[1:3]):          # block sums use atomics: order varies run to run
+            assert abs(a - b) <= 1e-13 * abs(b)
