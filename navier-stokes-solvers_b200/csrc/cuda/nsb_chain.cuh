@@ -170,7 +170,7 @@ __device__ __forceinline__ void chain_B_item(const NsbGeom &g, const ChainArgs &
 /* one comb pair by one warp. wb: this warp's NSB_CHG_WARP_BYTES; returns max |u|^2 seen */
 template <bool UMAX>
 __device__ __forceinline__ double chain_G_pair(const cd *z1base, const cd *z2base, cd *pout, unsigned char *wb,
-                                               const cd *TW, int lane) {
+                                               const cd *TW, int lane, const cd *znext = nullptr) {
     double *T = reinterpret_cast<double *>(wb);
     double *PK = reinterpret_cast<double *>(wb + 8192);
     double *PX = reinterpret_cast<double *>(wb + 8192 + 16384);
@@ -209,6 +209,10 @@ __device__ __forceinline__ double chain_G_pair(const cd *z1base, const cd *z2bas
             if (comb == 0) PK[m * 32 + lane] = J;
             else x[m] = cmk(PK[m * 32 + lane], J);
         }
+    }
+    if (znext != nullptr) { /* first input of this warp's NEXT pair (persistent kernel) */
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nsb_prefetch_l2(reinterpret_cast<const char *>(znext) + (lane * 4 + i) * 128);
     }
     nsb_fft1024_warp_sw<false>(x, T, TW, lane);
 #pragma unroll
@@ -552,6 +556,41 @@ __global__ void __launch_bounds__(256, 1) k_chain_G(NsbGeom g, ChainArgs a) {
     nsb_fill_tw1024(TW, g.WX, g.nx / 1024);
     __syncthreads();
     chain_G_item<UMAX>(a, raw + NSB_CH_TW_BYTES, TW, blockIdx.y % a.nslotZ, blockIdx.y % a.nslotP, blockIdx.x);
+}
+
+/* persistent G: grid = SMs, every warp walks pairs warp_global + k * total_warps of all slabs, so the
+ * twiddle table is built once per SM and the first (otherwise cold) input of the next pair is pulled
+ * towards L2 while the forward transform of the current one runs */
+template <bool UMAX>
+__global__ void __launch_bounds__(256, 1) k_chain_Gp(NsbGeom g, ChainArgs a) {
+    NSB_DYN_SMEM(unsigned char, raw);
+    cd *TW = reinterpret_cast<cd *>(raw);
+    nsb_fill_tw1024(TW, g.WX, g.nx / 1024);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int NP = a.NQ >> 1;
+    const long long total = (long long)a.nslab * NP, stride = (long long)gridDim.x * W;
+    unsigned char *wb = raw + NSB_CH_TW_BYTES + (size_t)warp * NSB_CHG_WARP_BYTES(UMAX);
+    double umax = 0.0;
+    for (long long p = (long long)blockIdx.x * W + warp; p < total; p += stride) {
+        const int slab = (int)(p / NP), pair = (int)(p - (long long)slab * NP);
+        const cd *z1 = a.Z + ((size_t)((slab % a.nslotZ) * 2 + 0) * a.NQ + 2 * pair) * 1024;
+        const cd *z2 = a.Z + ((size_t)((slab % a.nslotZ) * 2 + 1) * a.NQ + 2 * pair) * 1024;
+        cd *po = a.P + ((size_t)(slab % a.nslotP) * NP + pair) * 1024;
+        const cd *zn = nullptr;
+        if (p + stride < total) {
+            const long long q = p + stride;
+            const int s2 = (int)(q / NP), p2 = (int)(q - (long long)s2 * NP);
+            zn = a.Z + ((size_t)((s2 % a.nslotZ) * 2 + 0) * a.NQ + 2 * p2) * 1024;
+        }
+        const double u = chain_G_pair<UMAX>(z1, z2, po, wb, TW, lane, zn);
+        umax = fmax(umax, u);
+    }
+    if (UMAX) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, off));
+        if (lane == 0) atomicMax(a.umax_bits, (unsigned long long)__double_as_longlong(umax));
+    }
 }
 
 /* grid (nbatch, nslab) */
