@@ -129,6 +129,12 @@ int nsb_diagnostics(nsb_ctx *c, double out[4]);
 /* same sums from the device copies of the physical arrays U, V, OMEGA */
 int nsb_diagnostics_phys(nsb_ctx *c, double out[4]);
 
+/* The reductions over OMEGA_HAT that ns_spectral_check_resolution (spectral_analysis.c:36-66) and
+ * ns_spectral_analyze_convergence (:69-100) make, on the device: out = { sum |w|^2, sum |w|^2 over
+ * sqrt(k2)/sqrt(k2_last) > 0.8, max |w|, sum |w|^2 over k2 > 0.25 k2_last, number of such modes,
+ * k2_last } with k2_last = k2[nkx*nky - 1] as in the reference. Synchronous. */
+int nsb_spectral_stats(nsb_ctx *c, double out[6]);
+
 /* device-side scalars: last dt, time, number of steps taken. Synchronous. */
 int nsb_get_state(nsb_ctx *c, double *dt, double *t, int *steps);
 int nsb_set_time(nsb_ctx *c, double t);

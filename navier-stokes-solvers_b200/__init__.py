@@ -96,6 +96,7 @@ def load_nsb(path=None):
         "nsb_mgpu_import": [C.c_void_p, C.c_int, C.c_char_p],
         "nsb_mgpu_link_local": [C.POINTER(C.c_void_p), C.c_int],
         "nsb_mgpu_group_step": [C.POINTER(C.c_void_p), C.c_int, C.c_double],
+        "nsb_spectral_stats": [C.c_void_p, c_double_p],
         "nsb_mgpu_group_gather": [C.POINTER(C.c_void_p), C.c_int],
         "nsb_mgpu_group_scatter": [C.POINTER(C.c_void_p), C.c_int],
     }
@@ -231,6 +232,11 @@ class NsbContext:
         n = float(self.nx * self.ny)
         return {"energy": 0.5 * (out[0] + out[1]) / n, "enstrophy": 0.5 * out[2] / n,
                 "max_speed": float(np.sqrt(out[3]))}
+
+    def spectral_stats(self):
+        out = (C.c_double * 6)()
+        self._ck(self.lib.nsb_spectral_stats(self.h, out))
+        return dict(zip(["total", "high_k", "max_abs", "tail", "tail_modes", "k2_last"], out[:]))
 
     def state(self):
         dt, t, st = C.c_double(), C.c_double(), C.c_int()

@@ -1789,3 +1789,63 @@ extern "C" int nsb_mgpu_group_scatter(nsb_ctx **cs, int n) {
     }
     return 0;
 }
+
+/* ---------------------------------------------------- driver-loop spectral diagnostics */
+
+/* spectral_analysis.c:36-66 (check_resolution) and :69-100 (analyze_convergence) need four
+ * reductions over omega_hat; computed here so a LAZY-mode driver loop never downloads the field.
+ * out = { sum |w|^2, sum |w|^2 over sqrt(k2)/sqrt(k2_last) > 0.8, max |w|,
+ *         sum |w|^2 over k2 > 0.25 k2_last, number of such modes, k2_last } */
+__global__ void __launch_bounds__(256) k_spectral_stats(NsbGeom g, const cd *W, double *acc,
+                                                        unsigned long long *maxbits, unsigned long long *count) {
+    NSB_DYN_SMEM(double, red);
+    const size_t M = (size_t)g.nkx * g.ny;
+    const double kxl = g.kx[g.nkx - 1], kyl = g.ky[g.ny - 1];
+    const double k2_last = __dadd_rn(__dmul_rn(kxl, kxl), __dmul_rn(kyl, kyl));
+    const double max_k = __dsqrt_rn(k2_last);
+    double tot = 0.0, high = 0.0, peak = 0.0, tail = 0.0;
+    unsigned long long cnt = 0ull;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M; idx += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / g.nkx), i = (int)(idx - (size_t)j * g.nkx);
+        const cd w = W[idx];
+        const double mag = hypot(w.x, w.y);
+        const double mag2 = __dmul_rn(mag, mag);
+        const double kxv = g.kx[i], kyv = g.ky[j];
+        const double k2 = __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv));
+        tot += mag2;
+        const double kn = (max_k > 0.0) ? __ddiv_rn(__dsqrt_rn(k2), max_k) : 0.0;
+        if (kn > 0.8) high += mag2;
+        if (mag > peak) peak = mag;
+        if (k2 > 0.25 * k2_last) { tail += mag2; ++cnt; }
+    }
+    nsb_block_sum_to_global(tot, acc + 0, red);
+    nsb_block_sum_to_global(high, acc + 1, red);
+    nsb_block_sum_to_global(tail, acc + 2, red);
+    nsb_block_sum_to_global((double)cnt, acc + 3, red);
+    nsb_block_max_to_global(peak, maxbits, red);
+    (void)count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) acc[4] = k2_last;
+}
+
+extern "C" int nsb_spectral_stats(nsb_ctx *c, double out[6]) {
+    if (!c || !out) return fail("nsb_spectral_stats: null argument");
+    CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
+    void *w;
+    if (get_field(c, NSB_OMEGA_HAT, &w)) return -1;
+    CK(cudaMemsetAsync(c->d_sc->sums, 0, sizeof(double) * 4, c->stream));
+    CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->d_sc->stats, 0, sizeof(c->d_sc->stats), c->stream));
+    auto k = k_spectral_stats;
+    NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 256 * sizeof(double), c->stream, c->g, (const cd *)w,
+               c->d_sc->stats, &c->d_sc->umax_bits, (unsigned long long *)nullptr);
+    CKL();
+    c->launches++;
+    if (fetch_scalars(c)) return -1;
+    double peak;
+    memcpy(&peak, &c->h_sc->umax_bits, sizeof(double));
+    out[0] = c->h_sc->stats[0]; out[1] = c->h_sc->stats[1]; out[2] = peak;
+    out[3] = c->h_sc->stats[2]; out[4] = c->h_sc->stats[3]; out[5] = c->h_sc->stats[4];
+    CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
+    return 0;
+}

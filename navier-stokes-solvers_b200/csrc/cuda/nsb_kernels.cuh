@@ -707,6 +707,7 @@ struct NsbScalars {
     int step;
     double dt_hist[256];
     unsigned peer_flags[8];        /* device barrier of the slab decomposition: epoch announced by each peer */
+    double stats[8];               /* nsb_spectral_stats accumulators */
 };
 
 /* spectral_time_integration.c:22-30 : dt = clamp(min(cfl*dx/(|u|max+1e-12), 0.5*Re*dx^2)) */

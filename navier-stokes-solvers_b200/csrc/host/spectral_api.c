@@ -569,21 +569,39 @@ static void lazy_fetch_spectra(NSSpectralData *d, int with_velocity, const char 
 }
 
 /* spectral_analysis.c:36-66 */
-int ns_spectral_check_resolution(NSSpectralData *d) {
-    static const char *W = "ns_spectral_check_resolution";
-    ctx_of(d, W);
-    lazy_fetch_spectra(d, 0, W);
+/* reductions over omega_hat for the two driver-loop diagnostics: on the device in LAZY mode (no
+ * field download), over the host array otherwise */
+static void omega_hat_stats(NSSpectralData *d, double out[6], const char *where) {
+    if (lazy(d)) {
+        NSB_OK(nsb_spectral_stats(ctx_ro(d, where), out), where);
+        return;
+    }
     const size_t m = n_spec(d);
-    const double max_k = sqrt(d->k2[m - 1]);
-    double high = 0.0, total = 0.0;
+    const double k2_last = d->k2[m - 1];
+    const double max_k = sqrt(k2_last);
+    double total = 0.0, high = 0.0, peak = 0.0, tail = 0.0;
+    long cnt = 0;
     for (size_t k = 0; k < m; ++k) {
         const double a = cabs(d->omega_hat[k]);
         const double mag2 = a * a;
         total += mag2;
         const double kn = (max_k > 0.0) ? sqrt(d->k2[k]) / max_k : 0.0;
         if (kn > 0.8) high += mag2;
+        if (a > peak) peak = a;
+        if (d->k2[k] > 0.25 * k2_last) {
+            tail += mag2;
+            ++cnt;
+        }
     }
-    const double frac = (total > 1e-16) ? high / total : 0.0;
+    out[0] = total; out[1] = high; out[2] = peak; out[3] = tail; out[4] = (double)cnt; out[5] = k2_last;
+}
+
+int ns_spectral_check_resolution(NSSpectralData *d) {
+    static const char *W = "ns_spectral_check_resolution";
+    ctx_ro(d, W);
+    double st[6];
+    omega_hat_stats(d, st, W);
+    const double frac = (st[0] > 1e-16) ? st[1] / st[0] : 0.0;
     if (frac > 1e-6) {
         printf("Warning: %.2e%% of energy in high wavenumbers\n", frac * 100);
         return 0;
@@ -595,27 +613,16 @@ int ns_spectral_check_resolution(NSSpectralData *d) {
 void ns_spectral_analyze_convergence(NSSpectralData *d, int step) {
     static const char *W = "ns_spectral_analyze_convergence";
     if (step % 10 != 0) return;
-    ctx_of(d, W);
+    ctx_ro(d, W);
     double s[4];
     sums(d, s, W);
     const double energy = 0.5 * (s[0] + s[1]) / (d->nx * d->ny);
     const double enstrophy = 0.5 * s[2] / (d->nx * d->ny);
-    lazy_fetch_spectra(d, 0, W);
-    const size_t m = n_spec(d);
-    const double cut = 0.25 * d->k2[m - 1];
-    double peak = 0.0, tail = 0.0;
-    long high = 0;
-    for (size_t k = 0; k < m; ++k) {
-        const double a = cabs(d->omega_hat[k]);
-        if (a > peak) peak = a;
-        if (d->k2[k] > cut) {
-            tail += a * a;
-            ++high;
-        }
-    }
-    const double err = high > 0 ? sqrt(tail / (double)high) : 0.0;
+    double st[6];
+    omega_hat_stats(d, st, W);
+    const double err = st[4] > 0.0 ? sqrt(st[3] / st[4]) : 0.0;
     printf("Step %d: t=%.4f, E=%.6e, Ω=%.6e, max|ω̂|=%.2e, err=%.2e, dt=%.2e\n", step, d->t, energy, enstrophy,
-           peak, err, d->dt);
+           st[2], err, d->dt);
 }
 
 /* spectral_analysis.c:103-142 */

@@ -66,7 +66,7 @@ NSB_SYMBOLS = [
     "nsb_get_dt_history", "nsb_get_plan", "nsb_stream", "nsb_timer_start", "nsb_timer_stop", "nsb_profile_begin", "nsb_profile_end",
     "nsb_launch_count",
     "nsb_mgpu_setup", "nsb_mgpu_partition", "nsb_mgpu_export", "nsb_mgpu_import", "nsb_mgpu_link_local",
-    "nsb_mgpu_group_step", "nsb_mgpu_group_gather", "nsb_mgpu_group_scatter",
+    "nsb_mgpu_group_step", "nsb_mgpu_group_gather", "nsb_mgpu_group_scatter", "nsb_spectral_stats",
 ]
 
 

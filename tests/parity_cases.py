@@ -123,3 +123,24 @@ def check_free_running(nsb, lib, orc, kind, nx, ny, nsteps, every=10, hv=None, f
     c.close()
     o.close()
     return worst
+
+
+def check_spectral_stats(nsb, lib, nx, ny, **plan):
+    """nsb_spectral_stats against numpy over the same omega_hat (the reductions of
+    spectral_analysis.c:36-66 and :69-100)."""
+    rng = np.random.default_rng(17)
+    c = nsb.NsbContext(nx, ny, lib=lib, **plan)
+    w = rng.standard_normal((ny, nx // 2 + 1)) + 1j * rng.standard_normal((ny, nx // 2 + 1))
+    c.upload(nsb.OMEGA_HAT, w)
+    st = c.spectral_stats()
+    k2 = c.k2()
+    k2_last = k2.reshape(-1)[-1]
+    mag = np.abs(w)
+    kn = np.sqrt(k2) / np.sqrt(k2_last)
+    assert abs(st["k2_last"] - k2_last) <= 1e-12 * k2_last
+    assert abs(st["total"] - (mag ** 2).sum()) <= 1e-12 * (mag ** 2).sum()
+    assert abs(st["high_k"] - (mag[kn > 0.8] ** 2).sum()) <= 1e-12 * (mag ** 2).sum()
+    assert abs(st["max_abs"] - mag.max()) <= 1e-14 * mag.max()
+    assert abs(st["tail"] - (mag[k2 > 0.25 * k2_last] ** 2).sum()) <= 1e-12 * (mag ** 2).sum()
+    assert st["tail_modes"] == float((k2 > 0.25 * k2_last).sum())
+    c.close()

@@ -153,3 +153,7 @@ def test_emu_slab_decomposition_two_devices(nsb, emu_lib):
     grp.close()
     assert np.array_equal(got, ref)
     assert dts[0] == dts[1] == dt_ref
+
+
+def test_emu_spectral_stats(nsb, emu_lib):
+    pc.check_spectral_stats(nsb, emu_lib, 64, 32)

@@ -239,3 +239,9 @@ def test_host_backend_init_device_group(monkeypatch):
         assert got[3:] == ref[3:]                      # t, dt: bit-identical
         for a, b in zip(got[1:3], ref[1:3]):          # block sums use atomics: order varies run to run
             assert abs(a - b) <= 1e-13 * abs(b)
+
+
+def test_spectral_stats(nsb, cuda_lib):
+    """device-side reductions of the driver-loop diagnostics (no field download in LAZY mode)"""
+    pc.check_spectral_stats(nsb, cuda_lib, 512, 256)
+    pc.check_spectral_stats(nsb, cuda_lib, 2048, 2048)
