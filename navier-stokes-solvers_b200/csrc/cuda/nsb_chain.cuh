@@ -43,7 +43,8 @@ struct ChainArgs {
     int cb;      /* columns per device (the pitch of T') */
     cd *Z;       /* [slot][pp][q][1024] packed comb spectra */
     cd *P;       /* [slot][pair][1024] packed forward spectra */
-    int nslab;   /* own slabs: rowsT / 16 */
+    int nslab;   /* slabs of this launch */
+    int slab0;   /* first slab of this launch (slab ranges run concurrently on two streams) */
     int nslotZ, nslotP;
     int GY;      /* y1 values per slab = 16 / Y2 */
     int NQ;      /* combs per slab = 16 * X1 */
@@ -481,7 +482,10 @@ __device__ __forceinline__ void chain_B_step2x(const NsbGeom &g, const ChainArgs
  * is off the critical path with one CTA per SM.
  * smem: 2 stages x (2*16*nseg*BC complex) + 2 mbarriers (+128 B alignment slack).
  */
-template <int NT, int MINB>
+/* NST = 2: double buffered (B alone on the SM). NST = 1: one tile, the next item's copies are issued
+ * after the current item is done -- for the split chain, where the G warps that share the SM cover
+ * the copy latency and shared memory is what is scarce. */
+template <int NT, int MINB, int NST>
 __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a, const NSB_GRID_CONSTANT nsb_tmap tmT) {
     NSB_DYN_SMEM(cd, smem_raw);
     /* 128-byte alignment for the TMA destination. (Measured: keeping shared-memory provenance, i.e.
@@ -489,8 +493,8 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
     cd *smem = reinterpret_cast<cd *>((reinterpret_cast<size_t>(smem_raw) + 127) & ~(size_t)127);
     const int nseg = a.nd + a.nm;
     const size_t tile_elems = (size_t)2 * NSB_CH_ROWS * nseg * g.BC;
-    nsb_mbar_t *bars = reinterpret_cast<nsb_mbar_t *>(smem + 2 * tile_elems);
-    cd *twtab = smem + 2 * tile_elems + 4; /* BC * X1 x twiddles of the current batch */
+    nsb_mbar_t *bars = reinterpret_cast<nsb_mbar_t *>(smem + NST * tile_elems);
+    cd *twtab = smem + NST * tile_elems + 4; /* BC * X1 x twiddles of the current batch */
     if (threadIdx.x == 0) {
         nsb_mbar_init(&bars[0], 1);
         nsb_mbar_init(&bars[1], 1);
@@ -500,21 +504,22 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
     unsigned phase[2] = {0u, 0u};
     int item = blockIdx.x;
     if (item < nitems) {
-        const int slab = item / (2 * a.nbatch), rem = item - slab * 2 * a.nbatch;
-        chain_B_issue(g, a, &tmT, smem, &bars[0], slab, rem / a.nbatch, (rem % a.nbatch) * g.BC);
+        const int sl = item / (2 * a.nbatch), rem = item - sl * 2 * a.nbatch;
+        chain_B_issue(g, a, &tmT, smem, &bars[0], a.slab0 + sl, rem / a.nbatch, (rem % a.nbatch) * g.BC);
     }
     for (int n = 0; item < nitems; ++n, item += gridDim.x) {
-        const int st = n & 1;
+        const int st = (NST == 2) ? (n & 1) : 0;
         const int next = item + gridDim.x;
-        if (next < nitems) {
-            const int slab = next / (2 * a.nbatch), rem = next - slab * 2 * a.nbatch;
-            chain_B_issue(g, a, &tmT, smem + (size_t)(st ^ 1) * tile_elems, &bars[st ^ 1], slab, rem / a.nbatch,
+        if (NST == 2 && next < nitems) {
+            const int sl = next / (2 * a.nbatch), rem = next - sl * 2 * a.nbatch;
+            chain_B_issue(g, a, &tmT, smem + (size_t)(st ^ 1) * tile_elems, &bars[st ^ 1], a.slab0 + sl, rem / a.nbatch,
                           (rem % a.nbatch) * g.BC);
         }
         nsb_mbar_wait(&bars[st], phase[st]);
         phase[st] ^= 1u;
         cd *tile = smem + (size_t)st * tile_elems;
-        const int slab = item / (2 * a.nbatch), rem = item - slab * 2 * a.nbatch;
+        const int sl = item / (2 * a.nbatch), rem = item - sl * 2 * a.nbatch;
+        const int slab = a.slab0 + sl;
         const int pp = rem / a.nbatch, kb = (rem % a.nbatch) * g.BC;
         for (int w = threadIdx.x; w < g.BC * g.X1; w += blockDim.x) {
             const int cc = w / g.X1, x1 = w - cc * g.X1;
@@ -537,6 +542,10 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
             default: chain_B_step2x<16, true>(g, a, tile, slot, pp, kb, twtab); break;
         }
         __syncthreads(); /* the tile is free for the copies of item n+2 */
+        if (NST == 1 && next < nitems) {
+            const int sl2 = next / (2 * a.nbatch), rem2 = next - sl2 * 2 * a.nbatch;
+            chain_B_issue(g, a, &tmT, smem, &bars[0], a.slab0 + sl2, rem2 / a.nbatch, (rem2 % a.nbatch) * g.BC);
+        }
     }
 }
 
@@ -545,7 +554,7 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
 /* grid (nbatch, 2, nslab) */
 __global__ void __launch_bounds__(256, 2) k_chain_B(NsbGeom g, ChainArgs a) {
     NSB_DYN_SMEM(cd, tile);
-    chain_B_item(g, a, tile, blockIdx.z, blockIdx.z % a.nslotZ, blockIdx.y, blockIdx.x);
+    chain_B_item(g, a, tile, a.slab0 + blockIdx.z, (a.slab0 + blockIdx.z) % a.nslotZ, blockIdx.y, blockIdx.x);
 }
 
 /* grid (groups per slab, nslab), W warps */
@@ -555,7 +564,8 @@ __global__ void __launch_bounds__(256, 1) k_chain_G(NsbGeom g, ChainArgs a) {
     cd *TW = reinterpret_cast<cd *>(raw);
     nsb_fill_tw1024(TW, g.WX, g.nx / 1024);
     __syncthreads();
-    chain_G_item<UMAX>(a, raw + NSB_CH_TW_BYTES, TW, blockIdx.y % a.nslotZ, blockIdx.y % a.nslotP, blockIdx.x);
+    const int slab = a.slab0 + blockIdx.y;
+    chain_G_item<UMAX>(a, raw + NSB_CH_TW_BYTES, TW, slab % a.nslotZ, slab % a.nslotP, blockIdx.x);
 }
 
 /* persistent G: grid = SMs, every warp walks pairs warp_global + k * total_warps of all slabs, so the
@@ -573,14 +583,15 @@ __global__ void __launch_bounds__(256, 1) k_chain_Gp(NsbGeom g, ChainArgs a) {
     unsigned char *wb = raw + NSB_CH_TW_BYTES + (size_t)warp * NSB_CHG_WARP_BYTES(UMAX);
     double umax = 0.0;
     for (long long p = (long long)blockIdx.x * W + warp; p < total; p += stride) {
-        const int slab = (int)(p / NP), pair = (int)(p - (long long)slab * NP);
+        const int sl = (int)(p / NP), pair = (int)(p - (long long)sl * NP);
+        const int slab = a.slab0 + sl;
         const cd *z1 = a.Z + ((size_t)((slab % a.nslotZ) * 2 + 0) * a.NQ + 2 * pair) * 1024;
         const cd *z2 = a.Z + ((size_t)((slab % a.nslotZ) * 2 + 1) * a.NQ + 2 * pair) * 1024;
         cd *po = a.P + ((size_t)(slab % a.nslotP) * NP + pair) * 1024;
         const cd *zn = nullptr;
         if (p + stride < total) {
             const long long q = p + stride;
-            const int s2 = (int)(q / NP), p2 = (int)(q - (long long)s2 * NP);
+            const int s2 = a.slab0 + (int)(q / NP), p2 = (int)(q - (long long)(q / NP) * NP);
             zn = a.Z + ((size_t)((s2 % a.nslotZ) * 2 + 0) * a.NQ + 2 * p2) * 1024;
         }
         const double u = chain_G_pair<UMAX>(z1, z2, po, wb, TW, lane, zn);
@@ -596,7 +607,7 @@ __global__ void __launch_bounds__(256, 1) k_chain_Gp(NsbGeom g, ChainArgs a) {
 /* grid (nbatch, nslab) */
 __global__ void __launch_bounds__(256) k_chain_F(NsbGeom g, ChainArgs a) {
     NSB_DYN_SMEM(cd, tile);
-    chain_F_item(g, a, tile, blockIdx.y, blockIdx.y % a.nslotP, blockIdx.x);
+    chain_F_item(g, a, tile, a.slab0 + blockIdx.y, (a.slab0 + blockIdx.y) % a.nslotP, blockIdx.x);
 }
 
 /* ------------------------------------------------ the persistent dataflow kernel */

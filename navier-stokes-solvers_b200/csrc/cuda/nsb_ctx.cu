@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <set>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #define NSB_MIN_DT 1e-8 /* /root/reference/include/common_types.h:32 */
@@ -84,6 +86,11 @@ struct nsb_ctx {
     int tmT_ok, tmT8_ok;
     int ch_bbc;
     int ch_gpersist;
+    int ch_split_b, ch_split_ctas;
+    int ch_pieces;          /* slab ranges of the chain run on two streams (1 = one range, one stream) */
+    cudaStream_t stream2;
+    cd *bufP;               /* P of the split chain */
+    cudaEvent_t ch_ev[4];
     /* slab decomposition over the devices of one NVSwitch domain */
     int mg_rank, mg_world;
     int mg_cb, mg_c0, mg_c1;     /* columns per device, own column range */
@@ -98,7 +105,7 @@ struct nsb_ctx {
     cudaEvent_t mg_ev;
     int sm_count;
     long long launches;
-    std::set<const void *> *smem_set;
+    std::map<const void *, size_t> *smem_set; /* kernel -> dynamic shared memory size its attribute allows */
     cudaEvent_t ev0, ev1;
     /* optional per-kernel CUDA-event timing (nsb_profile_begin/_end) */
     int prof_on;
@@ -150,8 +157,14 @@ static int get_field(nsb_ctx *c, int f, void **out) {
 template <class K>
 static int ensure_smem(nsb_ctx *c, K kernel, size_t bytes, bool max_carveout = false) {
     if (bytes <= 48 * 1024 && !max_carveout) return 0;
-    const void *key = (const void *)kernel;
-    if (c->smem_set->count(key)) return 0;
+    /* the attribute belongs to the function (per device), not to a context: one process-wide table,
+     * only ever raised, so contexts with different tile sizes do not undercut each other */
+    static std::map<std::pair<int, const void *>, size_t> table;
+    static std::mutex table_mutex;
+    std::lock_guard<std::mutex> lock(table_mutex);
+    const std::pair<int, const void *> key(c->device, (const void *)kernel);
+    auto it = table.find(key);
+    if (it != table.end() && it->second >= bytes) return 0; /* the attribute already covers this launch */
     if (bytes > 227 * 1024) return fail("kernel needs %zu bytes of shared memory (> 227 KB)", bytes);
     if (bytes > 48 * 1024)
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -159,7 +172,7 @@ static int ensure_smem(nsb_ctx *c, K kernel, size_t bytes, bool max_carveout = f
      * costs 5-15 %, so only kernels that ask for it get it */
     if (max_carveout)
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    c->smem_set->insert(key);
+    table[key] = bytes;
     return 0;
 }
 
@@ -200,7 +213,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     memset(c->fields, 0, sizeof(c->fields));
     c->prm = *p;
     c->device = p->device;
-    c->smem_set = new std::set<const void *>();
+    c->smem_set = new std::map<const void *, size_t>();
     c->launches = 0;
     c->prof_on = 0;
     c->prof_ev = new std::vector<cudaEvent_t>();
@@ -237,6 +250,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->kW0 = c->kWst = c->kACC = c->kSFD = nullptr;
     c->k_truth = 0;
     c->chZ = c->chP = nullptr;
+    c->bufP = nullptr;
     c->tmT_ok = 0;
     c->tmT8_ok = 0;
     c->chCtr = nullptr;
@@ -253,6 +267,9 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->ch_ctas = env_int("NSB_CHAIN_CTAS", 2) == 2 ? 2 : 1;
     c->ch_btma = env_int("NSB_CHAIN_BTMA", 1);
     c->ch_bbc = env_int("NSB_CHAIN_BBC", -1);
+    c->ch_pieces = env_int("NSB_CHAIN_PIECES", 0);         /* 0 = automatic */
+    c->ch_split_b = env_int("NSB_CHAIN_SPLIT_B", 0);       /* 0: 8-column two-stage B, 1: 16-column one-stage B */
+    c->ch_split_ctas = env_int("NSB_CHAIN_SPLIT_CTAS", 2); /* B CTAs per SM in the split chain */
     c->ch_gpersist = env_int("NSB_CHAIN_GPERSIST", 0); /* measured: the persistent G is 6 % slower (2.93 vs 2.77 ms) */
     c->alpha_cols = env_int("NSB_ALPHA_COLS", 4) == 8 ? 8 : 4;
     c->alpha_tma = env_int("NSB_ALPHA_TMA", 1);
@@ -268,6 +285,8 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
 
     CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, p->device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    for (int k = 0; k < 4; ++k) CK(cudaEventCreateWithFlags(&c->ch_ev[k], cudaEventDisableTiming));
     CK(cudaMalloc((void **)&c->bufA, c->buf_elems * sizeof(cd)));
     CK(cudaMalloc((void **)&c->bufB, c->buf_elems * sizeof(cd)));
     CK(cudaMemset(c->bufA, 0, c->buf_elems * sizeof(cd)));
@@ -347,6 +366,7 @@ extern "C" void nsb_ctx_destroy(nsb_ctx *c) {
     for (int k = 0; k < c->mg_nopened; ++k) cudaIpcCloseMemHandle(c->mg_opened[k]);
     if (c->bufTp) cudaFree(c->bufTp);
     cudaEventDestroy(c->mg_ev);
+    if (c->bufP) cudaFree(c->bufP);
     if (c->chZ) cudaFree(c->chZ);
     if (c->chP) cudaFree(c->chP);
     if (c->chCtr) cudaFree(c->chCtr);
@@ -359,6 +379,8 @@ extern "C" void nsb_ctx_destroy(nsb_ctx *c) {
     }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->stream2);
+    for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ch_ev[k]);
     for (cudaEvent_t e : *c->prof_ev) cudaEventDestroy(e);
     delete c->prof_ev;
     delete c->prof_kind;
@@ -894,25 +916,41 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
     const size_t smemG = NSB_CH_TW_BYTES + (size_t)W * (want_umax ? NSB_CHG_WARP_BYTES(1) : NSB_CHG_WARP_BYTES(0));
     if (c->chain_mode == 1) {
         /* Z in bufB, P in bufA (T is dead once B has run), T' into the owners' exchange buffers */
-        a.nslotZ = a.nslotP = a.nslab;
+        const int total_slabs = a.nslab;
+        a.nslotZ = a.nslotP = total_slabs;
         a.Z = c->bufB;
         a.P = c->bufA;
-        if (c->ch_btma && 2 * tileB + 64 + 128 + twtab <= 227 * 1024 && 2 * g.BC <= 256) {
-            /* persistent, TMA-fed B: two shared-memory stages per CTA. With 8-column batches two
-             * 128-thread CTAs share an SM (each with the full register budget), so one CTA's
-             * step 1 overlaps the other's step 2 */
-            NsbGeom gB = g;
-            ChainArgs aB = a;
-            /* measured: 8-column batches win while the tile is small (4096^2: 0.31 vs 0.40 ms), 16-column
-             * batches with one 256-thread CTA per SM win at 16384^2 (3.56 vs 5.58 ms) */
-            const bool half = g.BC == 16 && (c->ch_bbc == 8 || (c->ch_bbc < 0 && tileB <= 48 * 1024));
-            if (half) {
-                gB.BC = 8;
-                aB.nbatch = (g.X2h + 1 + 7) / 8;
-            }
-            const size_t tB = half ? tileB / 2 : tileB;
-            const size_t smemB = 2 * tB + 64 + 128 + (half ? twtab / 2 : twtab);
-            nsb_tmap *tm = half ? &c->tmT8 : &c->tmT;
+        /* Pieces: the slabs are independent through B, G and F, so the chain can run as `pieces` slab
+         * ranges alternating between two streams, staggered so that the memory-bound B of one range
+         * shares the SMs with the FP64-bound G of the previous one. That needs CTAs small enough to
+         * co-reside: B with 8-column batches (128 threads, 2 x 45 KB) and G with 4 warps (112 KB). */
+        /* measured at 16384^2 (1024 slabs): 16 ranges 48.7 ms/step against 50.3 for one; at 4096^2 (256
+         * slabs) every split is slower. True co-residency (one B CTA + one G CTA per SM) was slower still:
+         * B needs all eight warps of an SM; the gain comes from overlapping the kernels' tails. */
+        int pieces = c->prof_on ? 1 : (c->ch_pieces > 0 ? c->ch_pieces : (total_slabs >= 512 ? 16 : 1));
+        if (pieces > total_slabs) pieces = total_slabs;
+        const bool split = pieces > 1;
+        if (split) {
+            /* P may no longer live in bufA: G of one range writes it while B of the next still reads T there */
+            if (!c->bufP) CK(cudaMalloc((void **)&c->bufP, (size_t)total_slabs * NP * 1024 * sizeof(cd)));
+            a.P = c->bufP;
+        }
+        const int Wg = split ? (want_umax ? 3 : 4) : W;
+        const size_t smemGp = NSB_CH_TW_BYTES + (size_t)Wg * (want_umax ? NSB_CHG_WARP_BYTES(1) : NSB_CHG_WARP_BYTES(0));
+        const bool use_tma = c->ch_btma && 2 * tileB + 64 + 128 + twtab <= 227 * 1024 && 2 * g.BC <= 256;
+        /* measured: 8-column batches win while the tile is small (4096^2: 0.31 vs 0.40 ms), 16-column
+         * batches with one 256-thread CTA per SM win at 16384^2 (3.56 vs 5.58 ms) when B runs alone */
+        const bool half = g.BC == 16 && ((split && c->ch_split_b == 0) || c->ch_bbc == 8 || (c->ch_bbc < 0 && tileB <= 48 * 1024));
+        /* split chain, large tiles: 16-column batches, ONE stage, 128 threads (fits beside a 4-warp G CTA) */
+        const bool single = split && !half && tileB + 64 + 128 + twtab <= 112 * 1024;
+        NsbGeom gB = g;
+        ChainArgs aB = a;
+        if (use_tma && half) {
+            gB.BC = 8;
+            aB.nbatch = (g.X2h + 1 + 7) / 8;
+        }
+        nsb_tmap *tm = half ? &c->tmT8 : &c->tmT;
+        if (use_tma) {
             int *tm_ok = half ? &c->tmT8_ok : &c->tmT_ok;
             if (!*tm_ok) {
                 if (make_tmap_2d(tm, c->bufA, (size_t)2 * g.PT, (size_t)4 * c->mg_rows, (size_t)g.PT * sizeof(cd),
@@ -920,60 +958,83 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
                     return -1;
                 *tm_ok = 1;
             }
-            prof_pre(c, PK_BETA_INV);
-            if (half) {
-                auto k = k_chain_B_tma<128, 2>;
-                if (ensure_smem(c, k, smemB, true)) return -1;
-                NSB_LAUNCH(k, dim3(2 * c->sm_count), dim3(128), smemB, c->stream, gB, aB, *tm);
+        }
+        const size_t tB = half ? tileB / 2 : tileB;
+        const size_t smemB = (single ? 1 : 2) * tB + 64 + 128 + (half ? twtab / 2 : twtab);
+        if (split) {
+            CK(cudaEventRecord(c->ch_ev[0], c->stream)); /* everything before the chain (alpha, barrier) */
+            CK(cudaStreamWaitEvent(c->stream2, c->ch_ev[0], 0));
+        }
+        for (int pc = 0; pc < pieces; ++pc) {
+            cudaStream_t st = (pc & 1) ? c->stream2 : c->stream;
+            const int s0 = (int)((long long)total_slabs * pc / pieces), s1 = (int)((long long)total_slabs * (pc + 1) / pieces);
+            a.slab0 = aB.slab0 = s0;
+            a.nslab = aB.nslab = s1 - s0;
+            /* stagger: B of this piece starts when B of the previous piece is done */
+            if (split && pc > 0) CK(cudaStreamWaitEvent(st, c->ch_ev[1 + ((pc - 1) & 1)], 0));
+            if (use_tma) {
+                prof_pre(c, PK_BETA_INV);
+                if (half) {
+                    auto k = k_chain_B_tma<128, 2, 2>;
+                    if (ensure_smem(c, k, smemB, true)) return -1;
+                    NSB_LAUNCH(k, dim3((split ? c->ch_split_ctas : 2) * c->sm_count), dim3(128), smemB, st, gB, aB, *tm);
+                } else if (single) {
+                    auto k = k_chain_B_tma<128, 2, 1>;
+                    if (ensure_smem(c, k, smemB, true)) return -1;
+                    NSB_LAUNCH(k, dim3(c->ch_split_ctas * c->sm_count), dim3(128), smemB, st, gB, aB, *tm);
+                } else {
+                    auto k = k_chain_B_tma<256, 1, 2>;
+                    if (ensure_smem(c, k, smemB, true)) return -1;
+                    NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), smemB, st, gB, aB, *tm);
+                }
+                prof_post(c);
             } else {
-                auto k = k_chain_B_tma<256, 1>;
-                if (ensure_smem(c, k, smemB, true)) return -1;
-                NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), smemB, c->stream, gB, aB, *tm);
+                auto k = k_chain_B;
+                if (ensure_smem(c, k, tileB, true)) return -1;
+                prof_pre(c, PK_BETA_INV);
+                NSB_LAUNCH(k, dim3(a.nbatch, 2, a.nslab), dim3(256), tileB, st, g, a);
+                prof_post(c);
+            }
+            CKL();
+            c->launches++;
+            if (split) CK(cudaEventRecord(c->ch_ev[1 + (pc & 1)], st));
+            const dim3 gridG((NP + Wg - 1) / Wg, a.nslab);
+            prof_pre(c, PK_GAMMA);
+            if (c->ch_gpersist && !split) {
+                if (want_umax) {
+                    auto k = k_chain_Gp<true>;
+                    if (ensure_smem(c, k, smemGp, true)) return -1;
+                    NSB_LAUNCH(k, dim3(c->sm_count), dim3(Wg * 32), smemGp, st, g, a);
+                } else {
+                    auto k = k_chain_Gp<false>;
+                    if (ensure_smem(c, k, smemGp, true)) return -1;
+                    NSB_LAUNCH(k, dim3(c->sm_count), dim3(Wg * 32), smemGp, st, g, a);
+                }
+            } else if (want_umax) {
+                auto k = k_chain_G<true>;
+                if (ensure_smem(c, k, smemGp, true)) return -1;
+                NSB_LAUNCH(k, gridG, dim3(Wg * 32), smemGp, st, g, a);
+            } else {
+                auto k = k_chain_G<false>;
+                if (ensure_smem(c, k, smemGp, true)) return -1;
+                NSB_LAUNCH(k, gridG, dim3(Wg * 32), smemGp, st, g, a);
             }
             prof_post(c);
             CKL();
             c->launches++;
-        } else {
-            auto k = k_chain_B;
-            if (ensure_smem(c, k, tileB, true)) return -1;
-            prof_pre(c, PK_BETA_INV);
-            NSB_LAUNCH(k, dim3(a.nbatch, 2, a.nslab), dim3(256), tileB, c->stream, g, a);
-            prof_post(c);
-            CKL();
-            c->launches++;
-        }
-        const dim3 gridG((NP + W - 1) / W, a.nslab);
-        prof_pre(c, PK_GAMMA);
-        if (c->ch_gpersist) {
-            if (want_umax) {
-                auto k = k_chain_Gp<true>;
-                if (ensure_smem(c, k, smemG, true)) return -1;
-                NSB_LAUNCH(k, dim3(c->sm_count), dim3(W * 32), smemG, c->stream, g, a);
-            } else {
-                auto k = k_chain_Gp<false>;
-                if (ensure_smem(c, k, smemG, true)) return -1;
-                NSB_LAUNCH(k, dim3(c->sm_count), dim3(W * 32), smemG, c->stream, g, a);
+            {
+                auto k = k_chain_F;
+                if (ensure_smem(c, k, tileF, true)) return -1;
+                prof_pre(c, PK_BETA_FWD);
+                NSB_LAUNCH(k, dim3(a.nbatch, a.nslab), dim3(256), tileF, st, g, a);
+                prof_post(c);
+                CKL();
+                c->launches++;
             }
-        } else if (want_umax) {
-            auto k = k_chain_G<true>;
-            if (ensure_smem(c, k, smemG, true)) return -1;
-            NSB_LAUNCH(k, gridG, dim3(W * 32), smemG, c->stream, g, a);
-        } else {
-            auto k = k_chain_G<false>;
-            if (ensure_smem(c, k, smemG, true)) return -1;
-            NSB_LAUNCH(k, gridG, dim3(W * 32), smemG, c->stream, g, a);
         }
-        prof_post(c);
-        CKL();
-        c->launches++;
-        {
-            auto k = k_chain_F;
-            if (ensure_smem(c, k, tileF, true)) return -1;
-            prof_pre(c, PK_BETA_FWD);
-            NSB_LAUNCH(k, dim3(a.nbatch, a.nslab), dim3(256), tileF, c->stream, g, a);
-            prof_post(c);
-            CKL();
-            c->launches++;
+        if (split) { /* the main stream continues when the other one has drained */
+            CK(cudaEventRecord(c->ch_ev[3], c->stream2));
+            CK(cudaStreamWaitEvent(c->stream, c->ch_ev[3], 0));
         }
         return 0;
     }
