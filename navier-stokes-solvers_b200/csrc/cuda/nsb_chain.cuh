@@ -482,10 +482,7 @@ __device__ __forceinline__ void chain_B_step2x(const NsbGeom &g, const ChainArgs
  * is off the critical path with one CTA per SM.
  * smem: 2 stages x (2*16*nseg*BC complex) + 2 mbarriers (+128 B alignment slack).
  */
-/* NST = 2: double buffered (B alone on the SM). NST = 1: one tile, the next item's copies are issued
- * after the current item is done -- for the split chain, where the G warps that share the SM cover
- * the copy latency and shared memory is what is scarce. */
-template <int NT, int MINB, int NST>
+template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a, const NSB_GRID_CONSTANT nsb_tmap tmT) {
     NSB_DYN_SMEM(cd, smem_raw);
     /* 128-byte alignment for the TMA destination. (Measured: keeping shared-memory provenance, i.e.
@@ -493,8 +490,8 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
     cd *smem = reinterpret_cast<cd *>((reinterpret_cast<size_t>(smem_raw) + 127) & ~(size_t)127);
     const int nseg = a.nd + a.nm;
     const size_t tile_elems = (size_t)2 * NSB_CH_ROWS * nseg * g.BC;
-    nsb_mbar_t *bars = reinterpret_cast<nsb_mbar_t *>(smem + NST * tile_elems);
-    cd *twtab = smem + NST * tile_elems + 4; /* BC * X1 x twiddles of the current batch */
+    nsb_mbar_t *bars = reinterpret_cast<nsb_mbar_t *>(smem + 2 * tile_elems);
+    cd *twtab = smem + 2 * tile_elems + 4; /* BC * X1 x twiddles of the current batch */
     if (threadIdx.x == 0) {
         nsb_mbar_init(&bars[0], 1);
         nsb_mbar_init(&bars[1], 1);
@@ -508,9 +505,9 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
         chain_B_issue(g, a, &tmT, smem, &bars[0], a.slab0 + sl, rem / a.nbatch, (rem % a.nbatch) * g.BC);
     }
     for (int n = 0; item < nitems; ++n, item += gridDim.x) {
-        const int st = (NST == 2) ? (n & 1) : 0;
+        const int st = n & 1;
         const int next = item + gridDim.x;
-        if (NST == 2 && next < nitems) {
+        if (next < nitems) {
             const int sl = next / (2 * a.nbatch), rem = next - sl * 2 * a.nbatch;
             chain_B_issue(g, a, &tmT, smem + (size_t)(st ^ 1) * tile_elems, &bars[st ^ 1], a.slab0 + sl, rem / a.nbatch,
                           (rem % a.nbatch) * g.BC);
@@ -542,10 +539,6 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
             default: chain_B_step2x<16, true>(g, a, tile, slot, pp, kb, twtab); break;
         }
         __syncthreads(); /* the tile is free for the copies of item n+2 */
-        if (NST == 1 && next < nitems) {
-            const int sl2 = next / (2 * a.nbatch), rem2 = next - sl2 * 2 * a.nbatch;
-            chain_B_issue(g, a, &tmT, smem, &bars[0], a.slab0 + sl2, rem2 / a.nbatch, (rem2 % a.nbatch) * g.BC);
-        }
     }
 }
 

@@ -86,7 +86,6 @@ struct nsb_ctx {
     int tmT_ok, tmT8_ok;
     int ch_bbc;
     int ch_gpersist;
-    int ch_split_b, ch_split_ctas;
     int ch_pieces;          /* slab ranges of the chain run on two streams (1 = one range, one stream) */
     cudaStream_t stream2;
     cd *bufP;               /* P of the split chain */
@@ -268,8 +267,6 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->ch_btma = env_int("NSB_CHAIN_BTMA", 1);
     c->ch_bbc = env_int("NSB_CHAIN_BBC", -1);
     c->ch_pieces = env_int("NSB_CHAIN_PIECES", 0);         /* 0 = automatic */
-    c->ch_split_b = env_int("NSB_CHAIN_SPLIT_B", 0);       /* 0: 8-column two-stage B, 1: 16-column one-stage B */
-    c->ch_split_ctas = env_int("NSB_CHAIN_SPLIT_CTAS", 2); /* B CTAs per SM in the split chain */
     c->ch_gpersist = env_int("NSB_CHAIN_GPERSIST", 0); /* measured: the persistent G is 6 % slower (2.93 vs 2.77 ms) */
     c->alpha_cols = env_int("NSB_ALPHA_COLS", 4) == 8 ? 8 : 4;
     c->alpha_tma = env_int("NSB_ALPHA_TMA", 1);
@@ -925,8 +922,9 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
          * shares the SMs with the FP64-bound G of the previous one. That needs CTAs small enough to
          * co-reside: B with 8-column batches (128 threads, 2 x 45 KB) and G with 4 warps (112 KB). */
         /* measured at 16384^2 (1024 slabs): 16 ranges 48.7 ms/step against 50.3 for one; at 4096^2 (256
-         * slabs) every split is slower. True co-residency (one B CTA + one G CTA per SM) was slower still:
-         * B needs all eight warps of an SM; the gain comes from overlapping the kernels' tails. */
+         * slabs) every split is slower. True co-residency (one B CTA + one G CTA per SM, also with a
+         * 16-column one-stage B) was slower still, 54-58 ms: B needs all eight warps of an SM; the gain
+         * comes from overlapping the kernels' tails. */
         int pieces = c->prof_on ? 1 : (c->ch_pieces > 0 ? c->ch_pieces : (total_slabs >= 512 ? 16 : 1));
         if (pieces > total_slabs) pieces = total_slabs;
         const bool split = pieces > 1;
@@ -940,9 +938,7 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
         const bool use_tma = c->ch_btma && 2 * tileB + 64 + 128 + twtab <= 227 * 1024 && 2 * g.BC <= 256;
         /* measured: 8-column batches win while the tile is small (4096^2: 0.31 vs 0.40 ms), 16-column
          * batches with one 256-thread CTA per SM win at 16384^2 (3.56 vs 5.58 ms) when B runs alone */
-        const bool half = g.BC == 16 && ((split && c->ch_split_b == 0) || c->ch_bbc == 8 || (c->ch_bbc < 0 && tileB <= 48 * 1024));
-        /* split chain, large tiles: 16-column batches, ONE stage, 128 threads (fits beside a 4-warp G CTA) */
-        const bool single = split && !half && tileB + 64 + 128 + twtab <= 112 * 1024;
+        const bool half = g.BC == 16 && (split || c->ch_bbc == 8 || (c->ch_bbc < 0 && tileB <= 48 * 1024));
         NsbGeom gB = g;
         ChainArgs aB = a;
         if (use_tma && half) {
@@ -960,7 +956,7 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
             }
         }
         const size_t tB = half ? tileB / 2 : tileB;
-        const size_t smemB = (single ? 1 : 2) * tB + 64 + 128 + (half ? twtab / 2 : twtab);
+        const size_t smemB = 2 * tB + 64 + 128 + (half ? twtab / 2 : twtab);
         if (split) {
             CK(cudaEventRecord(c->ch_ev[0], c->stream)); /* everything before the chain (alpha, barrier) */
             CK(cudaStreamWaitEvent(c->stream2, c->ch_ev[0], 0));
@@ -975,15 +971,11 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
             if (use_tma) {
                 prof_pre(c, PK_BETA_INV);
                 if (half) {
-                    auto k = k_chain_B_tma<128, 2, 2>;
+                    auto k = k_chain_B_tma<128, 2>;
                     if (ensure_smem(c, k, smemB, true)) return -1;
-                    NSB_LAUNCH(k, dim3((split ? c->ch_split_ctas : 2) * c->sm_count), dim3(128), smemB, st, gB, aB, *tm);
-                } else if (single) {
-                    auto k = k_chain_B_tma<128, 2, 1>;
-                    if (ensure_smem(c, k, smemB, true)) return -1;
-                    NSB_LAUNCH(k, dim3(c->ch_split_ctas * c->sm_count), dim3(128), smemB, st, gB, aB, *tm);
+                    NSB_LAUNCH(k, dim3(2 * c->sm_count), dim3(128), smemB, st, gB, aB, *tm);
                 } else {
-                    auto k = k_chain_B_tma<256, 1, 2>;
+                    auto k = k_chain_B_tma<256, 1>;
                     if (ensure_smem(c, k, smemB, true)) return -1;
                     NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), smemB, st, gB, aB, *tm);
                 }
