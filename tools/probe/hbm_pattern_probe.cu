@@ -69,6 +69,11 @@ int main() {
     run<false, true>("read, one segment per row (B boxes, 16 cols)", buf, nrows, row_bytes, row_bytes, 256);
     run<false, true>("read, one segment per row (8 cols)", buf, nrows, row_bytes, row_bytes, 128);
     run<false, true>("read, one segment per row (4 cols)", buf, nrows, row_bytes, row_bytes, 64);
+    // column-kernel-like for real: consecutive rows of a tile are 16 T rows (1.4 MB) apart, so nearly
+    // every row of a 1024-row tile lies in a different 2 MB page (TLB reach: 128 entries)
+    run<true, false>("write, tile rows 16 T-rows apart (alpha, 8 cols)", buf, nrows / 16, row_bytes, 16 * row_bytes, 128);
+    run<true, false>("write, tile rows 16 T-rows apart (alpha, 4 cols)", buf, nrows / 16, row_bytes, 16 * row_bytes, 64);
+    run<false, true>("read, tile rows 16 T-rows apart (alpha T' load, 8 cols)", buf, nrows / 16, row_bytes, 16 * row_bytes, 128);
     // Z-like: rows of 16 KB
     run<true, false>("write, 256 B per 16 KB row (Z)", buf, (nrows * row_bytes) / 16384, 16384, 16384, 256);
     run<true, true>("read+write same pattern 128 B", buf, nrows, row_bytes, row_bytes, 128);
