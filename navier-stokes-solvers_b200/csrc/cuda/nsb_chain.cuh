@@ -555,7 +555,7 @@ template <bool UMAX>
 __global__ void __launch_bounds__(256, 1) k_chain_G(NsbGeom g, ChainArgs a) {
     NSB_DYN_SMEM(unsigned char, raw);
     cd *TW = reinterpret_cast<cd *>(raw);
-    nsb_fill_tw1024(TW, g.WX, g.nx / 1024);
+    nsb_fill_tw1024(TW, g.TWX);
     __syncthreads();
     const int slab = a.slab0 + blockIdx.y;
     chain_G_item<UMAX>(a, raw + NSB_CH_TW_BYTES, TW, slab % a.nslotZ, slab % a.nslotP, blockIdx.x);
@@ -568,7 +568,7 @@ template <bool UMAX>
 __global__ void __launch_bounds__(256, 1) k_chain_Gp(NsbGeom g, ChainArgs a) {
     NSB_DYN_SMEM(unsigned char, raw);
     cd *TW = reinterpret_cast<cd *>(raw);
-    nsb_fill_tw1024(TW, g.WX, g.nx / 1024);
+    nsb_fill_tw1024(TW, g.TWX);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int NP = a.NQ >> 1;
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_chain(NsbGeom g, ChainArgs
     cd *TW = reinterpret_cast<cd *>(raw);
     unsigned char *ub = raw + NSB_CH_TW_BYTES;
     cd *tile = reinterpret_cast<cd *>(ub);
-    nsb_fill_tw1024(TW, g.WX, g.nx / 1024);
+    nsb_fill_tw1024(TW, g.TWX);
     const int W = blockDim.x >> 5;
     const int NP = a.NQ >> 1;
     const int nB = 2 * a.nbatch, nG = (NP + W - 1) / W, nF = a.nbatch;

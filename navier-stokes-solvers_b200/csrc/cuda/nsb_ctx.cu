@@ -55,7 +55,7 @@ struct nsb_ctx {
     cd *bufA, *bufB;
     size_t buf_elems;
     double *d_kx, *d_ky, *d_kyK;
-    cd *d_WY, *d_WX;
+    cd *d_WY, *d_WX, *d_TW;
     NsbScalars *d_sc;
     NsbScalars *h_sc; /* pinned */
     NsbHv hv;
@@ -324,6 +324,23 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     CK(cudaMalloc((void **)&c->d_WX, w.size() * sizeof(cd)));
     CK(cudaMemcpy(c->d_WX, w.data(), w.size() * sizeof(cd), cudaMemcpyHostToDevice));
     g.kx = c->d_kx; g.ky = c->d_ky; g.kyK = c->d_kyK; g.WY = c->d_WY; g.WX = c->d_WX;
+    {
+        /* the 1024 twiddles of the warp FFT in the order its CTAs stage them (entries of the same
+         * long-double tables: bit-identical to gathering them from WY / WX) */
+        std::vector<cd> tw(2048), wn;
+        for (int pass = 0; pass < 2; ++pass) {
+            const int n = pass ? g.nx : g.ny;
+            fill_twiddles(wn, n);
+            for (int k = 0; k < 1024; ++k) {
+                const int r = k >> 5, t = k & 31;
+                tw[pass * 1024 + k] = (n >= 1024) ? wn[(size_t)(r * t) * (n / 1024)] : make_double2(1.0, 0.0);
+            }
+        }
+        CK(cudaMalloc((void **)&c->d_TW, tw.size() * sizeof(cd)));
+        CK(cudaMemcpy(c->d_TW, tw.data(), tw.size() * sizeof(cd), cudaMemcpyHostToDevice));
+        g.TWY = c->d_TW;
+        g.TWX = c->d_TW + 1024;
+    }
 
     CK(cudaMalloc((void **)&c->d_sc, sizeof(NsbScalars)));
     CK(cudaMemset(c->d_sc, 0, sizeof(NsbScalars)));
@@ -367,7 +384,7 @@ extern "C" void nsb_ctx_destroy(nsb_ctx *c) {
     if (c->chZ) cudaFree(c->chZ);
     if (c->chP) cudaFree(c->chP);
     if (c->chCtr) cudaFree(c->chCtr);
-    cudaFree(c->d_kx); cudaFree(c->d_ky); cudaFree(c->d_kyK); cudaFree(c->d_WY); cudaFree(c->d_WX);
+    cudaFree(c->d_kx); cudaFree(c->d_ky); cudaFree(c->d_kyK); cudaFree(c->d_WY); cudaFree(c->d_WX); cudaFree(c->d_TW);
     cudaFree(c->d_sc); cudaFreeHost(c->h_sc);
     if (c->d_force) cudaFree(c->d_force);
     for (int s = 0; s < NSB_FORCE_RING; ++s) {

@@ -102,13 +102,12 @@ __device__ __forceinline__ void nsb_dft32(cd (&x)[32]) {
     }
 }
 
-/* fills TW[r*32 + t] = exp(-2 pi i t r / 1024) from a table W[e*wmul] = exp(-2 pi i e/1024);
+/* fills TW[r*32 + t] = exp(-2 pi i t r / 1024) from the per-context table TAB (the same 1024 values,
+ * already in this order: a contiguous, coalesced 16 KB copy instead of a gather with stride r*t from the
+ * length-n twiddle table, which every CTA of the column and comb kernels used to pay at start-up);
  * all threads of the CTA take part; caller syncs. */
-__device__ __forceinline__ void nsb_fill_tw1024(cd *TW, const cd *__restrict__ W, int wmul) {
-    for (int k = threadIdx.x; k < 1024; k += blockDim.x) {
-        const int r = k >> 5, t = k & 31;
-        TW[k] = __ldg(&W[(size_t)(r * t) * wmul]);
-    }
+__device__ __forceinline__ void nsb_fill_tw1024(cd *TW, const cd *__restrict__ TAB) {
+    for (int k = threadIdx.x; k < 1024; k += blockDim.x) TW[k] = __ldg(&TAB[k]);
 }
 
 /*

@@ -44,6 +44,7 @@ struct NsbGeom {
     const double *kx, *ky;
     const double *kyK; /* ky permuted for the fast column kernel: kyK[j2*Y1 + j1] = ky[j1*Y2 + j2] */
     const cd *WY, *WX; /* exp(-2 pi i m/ny), exp(-2 pi i m/nx) */
+    const cd *TWY, *TWX; /* warp FFT-1024 twiddles exp(-2 pi i t r/1024) at [r*32 + t] (ny, nx >= 1024 only) */
     double norm;       /* 1/(nx*ny) */
 };
 
@@ -828,7 +829,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gamma1024(NsbGeom g, GammaFas
     double *PJ = reinterpret_cast<double *>(wb + NSB_G1024_T_BYTES + 1024 * 16);
     cd *L = reinterpret_cast<cd *>(wb + NSB_G1024_T_BYTES + 1024 * 16 + 1024 * 8);
     nsb_mbar_t *bar = reinterpret_cast<nsb_mbar_t *>(wb + NSB_G1024_T_BYTES + 1024 * 16 + 1024 * 8 + NSB_G1024_L_BYTES);
-    nsb_fill_tw1024(TW, g.WX, g.nx / 1024);
+    nsb_fill_tw1024(TW, g.TWX);
     if (lane == 0) nsb_mbar_init(bar, 1);
     __syncthreads();
     const unsigned row_bytes = (unsigned)a.nvalid_in * 16u;
@@ -1048,7 +1049,7 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
     const int ic = ic0 + warp;
     const bool active = ic < a.c1;
     const int cc = threadIdx.x & (COLS - 1), rr = threadIdx.x / COLS; /* cooperative copies: COLS threads per row */
-    nsb_fill_tw1024(TW, g.WY, g.ny / 1024);
+    nsb_fill_tw1024(TW, g.TWY);
     if (threadIdx.x < 32) TB[threadIdx.x] = __ldg(&g.WY[(size_t)32 * j2 * threadIdx.x]);
     /* y twiddle exp(-2 pi i j2 y1/ny), y1 = lane + 32 m, factored as ta * TB[m] (measured: a full
      * 1024-entry table in shared memory costs more in lost L1 than the extra complex multiply) */
