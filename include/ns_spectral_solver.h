@@ -176,6 +176,24 @@ int ns_spectral_run_steps(NSSpectralData *data, int n, NSForcingState *forcing);
 int ns_spectral_initialize_random_phase(NSSpectralData *data, unsigned long long seed, double k0,
                                         double max_omega);
 
+/* ns_spectral_output_solution with every `stride`-th point in x and y (stride 1 = the reference's
+ * file; spectral_output.c:4-27). 0 / -1. */
+int ns_spectral_output_solution_strided(NSSpectralData *data, const char *filename, int stride);
+
+/* Shell sums behind ns_spectral_analyze_spectrum (spectral_analysis.c:103-142): ek_sum[b] = sum of
+ * 0.5 (|u_hat|^2 + |v_hat|^2), count[b] = modes with b = (int)(sqrt(k2) + 0.5) < nbins. Under
+ * NS_SYNC_LAZY computed on the device from omega_hat, no download. 0 / -1. */
+int ns_spectral_energy_spectrum(NSSpectralData *data, int nbins, double *ek_sum, int *count);
+
+/* Restartable state: omega_hat, the SFD filter state, t, dt and (forcing nullable) the forcing
+ * generator's stream position and coloured-noise state in one raw binary file; a run resumed with
+ * ns_spectral_load_state continues bit for bit like the uninterrupted one. The solver (and the
+ * forcing state) must have been set up for the same grid (band, type) before loading. The
+ * reference's HDF5 checkpoint (src/common/checkpoint.c:266-301) omits the filter and forcing
+ * state. 0 / -1 + ns_spectral_last_error() */
+int ns_spectral_save_state(NSSpectralData *data, const NSForcingState *forcing, const char *filename);
+int ns_spectral_load_state(NSSpectralData *data, NSForcingState *forcing, const char *filename);
+
 /* last error text of the calling thread ("" if none) */
 const char *ns_spectral_last_error(void);
 /* the nsb context behind `data` (include/nsb.h), NULL before initialize_fft_plans */

@@ -135,6 +135,11 @@ int nsb_diagnostics_phys(nsb_ctx *c, double out[4]);
  * k2_last } with k2_last = k2[nkx*nky - 1] as in the reference. Synchronous. */
 int nsb_spectral_stats(nsb_ctx *c, double out[6]);
 
+/* ns_spectral_analyze_spectrum (spectral_analysis.c:103-142) without downloading omega_hat, u_hat,
+ * v_hat: ek_sum[b] = sum of 0.5 (|u_hat|^2 + |v_hat|^2) and count[b] = number of modes over the
+ * shell b = (int)(sqrt(k2) + 0.5), b < nbins (host arrays of nbins entries). Synchronous. */
+int nsb_energy_spectrum(nsb_ctx *c, int nbins, double *ek_sum, int *count);
+
 /* device-side scalars: last dt, time, number of steps taken. Synchronous. */
 int nsb_get_state(nsb_ctx *c, double *dt, double *t, int *steps);
 int nsb_set_time(nsb_ctx *c, double t);

@@ -1919,3 +1919,73 @@ extern "C" int nsb_spectral_stats(nsb_ctx *c, double out[6]) {
     CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
     return 0;
 }
+
+/* spectral_analysis.c:103-142 (analyze_spectrum): shell sums of 0.5 (|u_hat|^2 + |v_hat|^2) with
+ * bin = (int)(sqrt(k2) + 0.5) < nbins, and the number of modes per shell, straight from omega_hat
+ * (psi_hat, u_hat, v_hat per mode as in spectral_core.c:8-34; nothing is materialised or downloaded).
+ * A warp covers 32 consecutive kx of one ky row, where the shell index is non-decreasing: equal
+ * neighbours are combined by a segmented shuffle scan, so one atomic per (warp, shell) reaches L2. */
+__global__ void __launch_bounds__(256) k_energy_spectrum(NsbGeom g, const cd *W, int nbins, double *ek, int *cnt) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int chunks = (g.nkx + 31) >> 5;
+    const size_t nwork = (size_t)g.ny * chunks;
+    for (size_t wk = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); wk < nwork; wk += (size_t)gridDim.x * wpb) {
+        const int j = (int)(wk / chunks), i = (int)(wk - (size_t)j * chunks) * 32 + lane;
+        int bin = -1;
+        double e = 0.0;
+        if (i < g.nkx) {
+            const double kxv = g.kx[i], kyv = g.ky[j];
+            const double k2 = __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv));
+            const int b = (int)(__dsqrt_rn(k2) + 0.5);
+            if (b < nbins) {
+                const cd p = nsb_psi_from_w(W[(size_t)j * g.nkx + i], k2);
+                const cd u = nsb_ik(kyv, p), v = nsb_ik(kxv, p);
+                const double a = hypot(u.x, u.y), c = hypot(v.x, v.y);
+                e = 0.5 * __dadd_rn(__dmul_rn(a, a), __dmul_rn(c, c));
+                bin = b;
+            }
+        }
+        double n = bin >= 0 ? 1.0 : 0.0;
+        const double bd = (double)bin;
+        /* segmented inclusive scan over runs of equal `bin` */
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int src = lane >= off ? lane - off : lane;
+            const double eo = __shfl_sync(0xffffffffu, e, src);
+            const double no = __shfl_sync(0xffffffffu, n, src);
+            const double bo = __shfl_sync(0xffffffffu, bd, src);
+            if (lane >= off && bo == bd) { e += eo; n += no; }
+        }
+        const double bnext = __shfl_sync(0xffffffffu, bd, lane < 31 ? lane + 1 : lane);
+        if (bin >= 0 && (lane == 31 || bnext != bd)) {
+            atomicAdd(&ek[bin], e);
+            atomicAdd(&cnt[bin], (int)n);
+        }
+    }
+}
+
+extern "C" int nsb_energy_spectrum(nsb_ctx *c, int nbins, double *ek_sum, int *count) {
+    if (!c || !ek_sum || !count || nbins <= 0) return fail("nsb_energy_spectrum: bad argument");
+    CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
+    void *w;
+    if (get_field(c, NSB_OMEGA_HAT, &w)) return -1;
+    double *d_ek = nullptr;
+    const size_t bytes = (size_t)nbins * (sizeof(double) + sizeof(int));
+    CK(cudaMalloc((void **)&d_ek, bytes));
+    int *d_cnt = reinterpret_cast<int *>(d_ek + nbins);
+    cudaError_t e = cudaMemsetAsync(d_ek, 0, bytes, c->stream);
+    if (e == cudaSuccess) {
+        auto k = k_energy_spectrum;
+        NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 0, c->stream, c->g, (const cd *)w, nbins, d_ek, d_cnt);
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ek_sum, d_ek, (size_t)nbins * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(count, d_cnt, (size_t)nbins * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_ek);
+    if (e != cudaSuccess) return fail("nsb_energy_spectrum: %s", cudaGetErrorString(e));
+    return 0;
+}

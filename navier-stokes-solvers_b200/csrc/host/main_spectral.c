@@ -19,6 +19,8 @@
  *   spectral.sfd.strength [0 = off]  spectral.sfd.timescale [1]
  *   init.type taylor_green|random_phase [taylor_green]  init.seed [7]  init.k0 [8]
  *   init.max_omega [5]   output.interval [50, 0 = none]  output.prefix [spectral_solution]
+ *   output.stride [0 = automatic: smallest power of two that keeps a dump <= 1024 x 1024 points]
+ *   restart.load [none] (resume from this file)  restart.save [none]  restart.interval [0 = only at the end]
  *   backend.device [0]   backend.gpus [1] (slab decomposition over devices device..device+gpus-1)
  */
 #include "ns_config.h"
@@ -73,6 +75,8 @@ static int load_config(int argc, char **argv, NSConfig *cfg) {
         {"spectral.hyperviscosity.cutoff_ratio", NS_CONFIG_VALUE_DOUBLE, 0, 0, 1, 1, 1, NULL, 0},
         {"init.type", NS_CONFIG_VALUE_STRING, 0, 0, 0, 0, 0, init_ok, 2},
         {"output.interval", NS_CONFIG_VALUE_INT, 0, 0, 0, 1, 0, NULL, 0},
+        {"output.stride", NS_CONFIG_VALUE_INT, 0, 0, 0, 1, 0, NULL, 0},
+        {"restart.interval", NS_CONFIG_VALUE_INT, 0, 0, 0, 1, 0, NULL, 0},
         {"backend.device", NS_CONFIG_VALUE_INT, 0, 0, 0, 1, 0, NULL, 0},
         {"backend.gpus", NS_CONFIG_VALUE_INT, 0, 1, 8, 1, 1, NULL, 0},
     };
@@ -109,6 +113,13 @@ int main(int argc, char *argv[]) {
     const int max_steps = ns_config_get_int(&cfg, "time.max_steps", 0);
     const int output_interval = ns_config_get_int(&cfg, "output.interval", 50);
     const char *prefix = ns_config_get_string(&cfg, "output.prefix", "spectral_solution");
+    /* a full ASCII dump is 76 bytes per point (20 GB at 16384^2): thin it out by default */
+    int out_stride = ns_config_get_int(&cfg, "output.stride", 0);
+    if (out_stride <= 0)
+        for (out_stride = 1; (nx > ny ? nx : ny) / out_stride > 1024; out_stride *= 2) {}
+    const char *restart_load = ns_config_get_string(&cfg, "restart.load", "");
+    const char *restart_save = ns_config_get_string(&cfg, "restart.save", "");
+    const int restart_interval = ns_config_get_int(&cfg, "restart.interval", 0);
 
     printf("Resolution: %dx%d modes\n", nx, ny);
     printf("Domain: [0,%.2f] x [0,%.2f]\n", Lx, Ly);
@@ -174,6 +185,14 @@ int main(int argc, char *argv[]) {
         fs = &forcing;
     }
 
+    if (restart_load[0]) {
+        if (ns_spectral_load_state(data, fs, restart_load) != 0) {
+            fprintf(stderr, "restart.load: %s\n", ns_spectral_last_error());
+            ns_spectral_free(data);
+            return 2;
+        }
+        printf("Resumed from %s at t = %.6f\n", restart_load, data->t);
+    }
     ns_spectral_compute_derivatives(data); /* canonical start: psi_hat defined */
     printf("Initial conditions:\n");
     printf("Energy: %.6e\n", ns_spectral_compute_energy(data));
@@ -199,9 +218,12 @@ int main(int argc, char *argv[]) {
         if (output_interval > 0 && step % output_interval == 0) {
             char filename[512];
             snprintf(filename, sizeof filename, "%s_step_%04d.dat", prefix, step);
-            ns_spectral_output_solution(data, filename);
+            ns_spectral_output_solution_strided(data, filename, out_stride);
             if (step % (5 * output_interval) == 0) ns_spectral_analyze_spectrum(data);
         }
+        if (restart_save[0] && restart_interval > 0 && step % restart_interval == 0 &&
+            ns_spectral_save_state(data, fs, restart_save) != 0)
+            fprintf(stderr, "restart.save: %s\n", ns_spectral_last_error());
         if (data->dt < MIN_DT) {
             printf("Time step too small!\n");
             break;
@@ -222,8 +244,10 @@ int main(int argc, char *argv[]) {
     if (output_interval > 0) {
         char filename[512];
         snprintf(filename, sizeof filename, "%s_final.dat", prefix);
-        ns_spectral_output_solution(data, filename);
+        ns_spectral_output_solution_strided(data, filename, out_stride);
     }
+    if (restart_save[0] && ns_spectral_save_state(data, fs, restart_save) != 0)
+        fprintf(stderr, "restart.save: %s\n", ns_spectral_last_error());
     ns_spectral_analyze_spectrum(data);
 
     printf("\nSpectral Accuracy:\n");

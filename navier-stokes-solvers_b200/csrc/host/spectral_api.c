@@ -625,27 +625,39 @@ void ns_spectral_analyze_convergence(NSSpectralData *d, int step) {
            st[2], err, d->dt);
 }
 
-/* spectral_analysis.c:103-142 */
+/* spectral_analysis.c:103-142. LAZY: shell sums on the device (nsb_energy_spectrum), nothing is
+ * downloaded; EAGER: over the host u_hat, v_hat like the reference. */
+int ns_spectral_energy_spectrum(NSSpectralData *d, int nbins, double *ek_sum, int *count) {
+    static const char *W = "ns_spectral_energy_spectrum";
+    if (!d || nbins <= 0 || !ek_sum || !count) return -1;
+    if (lazy(d)) {
+        NSB_OK(nsb_energy_spectrum(ctx_ro(d, W), nbins, ek_sum, count), W);
+        return 0;
+    }
+    memset(ek_sum, 0, (size_t)nbins * sizeof(double));
+    memset(count, 0, (size_t)nbins * sizeof(int));
+    for (size_t k = 0; k < n_spec(d); ++k) {
+        const int bin = (int)(sqrt(d->k2[k]) + 0.5);
+        if (bin < nbins) {
+            const double a = cabs(d->u_hat[k]), b = cabs(d->v_hat[k]);
+            ek_sum[bin] += 0.5 * (a * a + b * b);
+            count[bin]++;
+        }
+    }
+    return 0;
+}
+
 void ns_spectral_analyze_spectrum(NSSpectralData *d) {
     static const char *W = "ns_spectral_analyze_spectrum";
-    ctx_of(d, W);
-    lazy_fetch_spectra(d, 1, W);
+    ctx_ro(d, W);
     const int nkx = d->nkx, nky = d->nky;
     const int max_k = (int)fmin(nkx, nky / 2);
     double *ek = (double *)calloc((size_t)max_k, sizeof(double));
     int *cnt = (int *)calloc((size_t)max_k, sizeof(int));
-    if (!ek || !cnt) {
+    if (!ek || !cnt || ns_spectral_energy_spectrum(d, max_k, ek, cnt) != 0) {
         free(ek);
         free(cnt);
         return;
-    }
-    for (size_t k = 0; k < n_spec(d); ++k) {
-        const int bin = (int)(sqrt(d->k2[k]) + 0.5);
-        if (bin < max_k) {
-            const double a = cabs(d->u_hat[k]), b = cabs(d->v_hat[k]);
-            ek[bin] += 0.5 * (a * a + b * b);
-            cnt[bin]++;
-        }
     }
     printf("\nEnergy Spectrum (t=%.4f):\n", d->t);
     printf("k\tE(k)\t\tSlope\n");
@@ -753,12 +765,15 @@ void ns_spectral_hyperviscosity_post_step(NSSpectralData *d, const fftw_complex 
 
 /* ------------------------------------------------------------------ output */
 
-/* spectral_output.c:4-27 */
-void ns_spectral_output_solution(NSSpectralData *d, const char *filename) {
+/* spectral_output.c:4-27 with every `stride`-th point in x and y (stride 1 = the reference's file,
+ * byte for byte the same format: scripts/plot_solution.py and energy_spectrum.py read it). A full
+ * ASCII dump is 76 bytes per point, 20 GB at 16384^2, hence the stride. */
+int ns_spectral_output_solution_strided(NSSpectralData *d, const char *filename, int stride) {
     static const char *W = "ns_spectral_output_solution";
     nsb_ctx *c = ctx_ro(d, W);
+    if (!filename || stride < 1) return -1;
     FILE *fp = fopen(filename, "w");
-    if (!fp) return;
+    if (!fp) return -1;
     if (lazy(d)) {
         NSB_OK(nsb_compute_derivatives(c), W);
         download(d, NSB_U, d->u, W);
@@ -772,15 +787,158 @@ void ns_spectral_output_solution(NSSpectralData *d, const char *filename) {
     download(d, NSB_PSI, d->psi, W);
     fprintf(fp, "# Spectral Navier-Stokes Solution\n");
     fprintf(fp, "# x y u v omega psi\n");
-    for (int j = 0; j < d->ny; ++j) {
-        for (int i = 0; i < d->nx; ++i) {
+    for (int j = 0; j < d->ny; j += stride) {
+        for (int i = 0; i < d->nx; i += stride) {
             const size_t idx = (size_t)j * d->nx + i;
             fprintf(fp, "%.8f %.8f %.8e %.8e %.8e %.8e\n", d->x[i], d->y[j], d->u[idx], d->v[idx], d->omega[idx],
                     d->psi[idx]);
         }
         fprintf(fp, "\n");
     }
+    return fclose(fp) == 0 ? 0 : -1;
+}
+
+/* spectral_output.c:4-27 */
+void ns_spectral_output_solution(NSSpectralData *d, const char *filename) {
+    (void)ns_spectral_output_solution_strided(d, filename, 1);
+}
+
+/* -------------------------------------------------------------- restartable state */
+
+/*
+ * Raw binary restart file. The reference's HDF5 checkpoint
+ * (src/common/checkpoint.c:266-301) stores u, v, omega, psi and three spectra but neither the SFD
+ * state nor the forcing stream, so a forced run cannot resume bit for bit from it. Here exactly the
+ * state the time loop owns is kept: omega_hat, sfd_hat (if the filter is on), t, dt, and of the
+ * forcing generator rng_state, have_spare, spare_gaussian and the coloured-noise state. A resumed
+ * run reproduces the uninterrupted one bit for bit (tests/test_host_api.py).
+ * Layout: NSRestartHeader | omega_hat[M] | sfd_hat[M] if has_sfd | colored_state[M] if has_colored.
+ */
+typedef struct {
+    char magic[8]; /* "NSBRST1\0" */
+    int nx, ny;
+    double Lx, Ly, Re, t, dt, cfl_factor;
+    NSSpectralHyperviscosityConfig hv;
+    int has_sfd, has_forcing, has_colored, pad_;
+    NSForcingConfig fcfg;
+    unsigned long long rng_state;
+    double spare_gaussian;
+    unsigned int have_spare;
+    int active_modes;
+} NSRestartHeader;
+
+static int write_all(FILE *fp, const void *p, size_t bytes) {
+    const char *q = (const char *)p;
+    while (bytes > 0) { /* chunks: a single fwrite of > 2 GB is not portable */
+        const size_t n = bytes > ((size_t)1 << 30) ? ((size_t)1 << 30) : bytes;
+        if (fwrite(q, 1, n, fp) != n) return -1;
+        q += n;
+        bytes -= n;
+    }
+    return 0;
+}
+
+static int read_all(FILE *fp, void *p, size_t bytes) {
+    char *q = (char *)p;
+    while (bytes > 0) {
+        const size_t n = bytes > ((size_t)1 << 30) ? ((size_t)1 << 30) : bytes;
+        if (fread(q, 1, n, fp) != n) return -1;
+        q += n;
+        bytes -= n;
+    }
+    return 0;
+}
+
+int ns_spectral_save_state(NSSpectralData *d, const NSForcingState *fs, const char *filename) {
+    static const char *W = "ns_spectral_save_state";
+    if (!d || !filename) { set_error("%s: NULL argument", W); return -1; }
+    ctx_ro(d, W);
+    const NSSpectralHyperviscosityConfig *h = &d->hyperviscosity;
+    const int sfd = (h->sfd_enabled && h->sfd_strength > 0.0);
+    if (lazy(d)) { /* the device copy is the truth */
+        download(d, NSB_OMEGA_HAT, d->omega_hat, W);
+        if (sfd) download(d, NSB_SFD_HAT, d->sfd_hat, W);
+        int steps;
+        NSB_OK(nsb_get_state(ctx_ro(d, W), &d->dt, &d->t, &steps), W);
+    }
+    NSRestartHeader hd;
+    memset(&hd, 0, sizeof hd);
+    memcpy(hd.magic, "NSBRST1", 8);
+    hd.nx = d->nx; hd.ny = d->ny;
+    hd.Lx = d->Lx; hd.Ly = d->Ly; hd.Re = d->Re; hd.t = d->t; hd.dt = d->dt; hd.cfl_factor = d->cfl_factor;
+    hd.hv = *h;
+    hd.has_sfd = sfd;
+    if (fs) {
+        if (fs->nkx != d->nkx || fs->nky != d->nky) { set_error("%s: forcing state does not match the grid", W); return -1; }
+        hd.has_forcing = 1;
+        hd.has_colored = (fs->config.type == NS_FORCING_COLORED_NOISE && fs->colored_state != NULL);
+        hd.fcfg = fs->config;
+        hd.rng_state = fs->rng_state;
+        hd.spare_gaussian = fs->spare_gaussian;
+        hd.have_spare = fs->have_spare;
+        hd.active_modes = fs->active_modes;
+    }
+    FILE *fp = fopen(filename, "wb");
+    if (!fp) { set_error("%s: cannot open %s", W, filename); return -1; }
+    const size_t mb = n_spec(d) * sizeof(fftw_complex);
+    int rc = write_all(fp, &hd, sizeof hd);
+    if (rc == 0) rc = write_all(fp, d->omega_hat, mb);
+    if (rc == 0 && hd.has_sfd) rc = write_all(fp, d->sfd_hat, mb);
+    if (rc == 0 && hd.has_colored) rc = write_all(fp, fs->colored_state, mb);
+    if (fclose(fp) != 0) rc = -1;
+    if (rc != 0) set_error("%s: short write to %s", W, filename);
+    return rc;
+}
+
+int ns_spectral_load_state(NSSpectralData *d, NSForcingState *fs, const char *filename) {
+    static const char *W = "ns_spectral_load_state";
+    if (!d || !filename) { set_error("%s: NULL argument", W); return -1; }
+    nsb_ctx *c = ctx_of(d, W);
+    FILE *fp = fopen(filename, "rb");
+    if (!fp) { set_error("%s: cannot open %s", W, filename); return -1; }
+    NSRestartHeader hd;
+    if (read_all(fp, &hd, sizeof hd) != 0 || memcmp(hd.magic, "NSBRST1", 8) != 0) {
+        fclose(fp);
+        set_error("%s: %s is not a restart file", W, filename);
+        return -1;
+    }
+    if (hd.nx != d->nx || hd.ny != d->ny || hd.Lx != d->Lx || hd.Ly != d->Ly) {
+        fclose(fp);
+        set_error("%s: file holds a %d x %d grid on %g x %g, the solver has %d x %d on %g x %g", W, hd.nx, hd.ny, hd.Lx,
+                  hd.Ly, d->nx, d->ny, d->Lx, d->Ly);
+        return -1;
+    }
+    if (fs && hd.has_forcing &&
+        (fs->nkx != d->nkx || fs->nky != d->nky || fs->active_modes != hd.active_modes ||
+         fs->config.type != hd.fcfg.type || (hd.has_colored && !fs->colored_state))) {
+        fclose(fp);
+        set_error("%s: forcing state was initialised with a different band or type than the file's", W);
+        return -1;
+    }
+    const size_t mb = n_spec(d) * sizeof(fftw_complex);
+    int rc = read_all(fp, d->omega_hat, mb);
+    if (rc == 0 && hd.has_sfd) rc = read_all(fp, d->sfd_hat, mb);
+    if (rc == 0 && hd.has_colored) {
+        if (fs && hd.has_forcing) rc = read_all(fp, fs->colored_state, mb);
+    }
     fclose(fp);
+    if (rc != 0) { set_error("%s: %s is truncated", W, filename); return -1; }
+    d->t = hd.t; d->dt = hd.dt; d->cfl_factor = hd.cfl_factor;
+    /* hyperviscosity_set would reseed sfd_hat from omega_hat (hyperviscosity.c:53-56): restore the
+     * configuration and weights without touching the filter state */
+    d->hyperviscosity = hd.hv;
+    ns_spectral_hyperviscosity_update_weights(d);
+    upload(d, NSB_OMEGA_HAT, d->omega_hat, W);
+    if (hd.has_sfd) upload(d, NSB_SFD_HAT, d->sfd_hat, W);
+    NSB_OK(nsb_set_time(c, d->t), W);
+    if (fs && hd.has_forcing) {
+        fs->config = hd.fcfg;
+        fs->rng_state = hd.rng_state;
+        fs->spare_gaussian = hd.spare_gaussian;
+        fs->have_spare = hd.have_spare;
+    }
+    if (!lazy(d)) refresh_derived_to_host(d, W);
+    return 0;
 }
 
 /* ---------------------------------------------------------------- additive */

@@ -49,6 +49,8 @@ SPECTRAL_SYMBOLS = [
     "ns_spectral_sync_to_host", "ns_spectral_sync_to_device", "ns_spectral_advance_rk4_forced",
     "ns_spectral_run_steps", "ns_spectral_initialize_random_phase", "ns_spectral_last_error",
     "ns_spectral_backend_context", "ns_spectral_backend_init",
+    "ns_spectral_output_solution_strided", "ns_spectral_energy_spectrum", "ns_spectral_save_state",
+    "ns_spectral_load_state",
 ]
 FORCING_SYMBOLS = ["ns_forcing_config_default", "ns_forcing_state_init", "ns_forcing_state_free",
                    "ns_forcing_generate", "ns_forcing_box_extent", "ns_forcing_active_indices",
@@ -67,6 +69,7 @@ NSB_SYMBOLS = [
     "nsb_launch_count",
     "nsb_mgpu_setup", "nsb_mgpu_partition", "nsb_mgpu_export", "nsb_mgpu_import", "nsb_mgpu_link_local",
     "nsb_mgpu_group_step", "nsb_mgpu_group_gather", "nsb_mgpu_group_scatter", "nsb_spectral_stats",
+    "nsb_energy_spectrum",
 ]
 
 
@@ -114,6 +117,10 @@ def load(path):
     lib.ns_spectral_initialize_random_phase.argtypes = [SP, C.c_ulonglong, C.c_double, C.c_double]
     lib.ns_spectral_last_error.restype = C.c_char_p
     lib.ns_spectral_backend_init.argtypes = [SP, C.c_int]
+    lib.ns_spectral_output_solution_strided.argtypes = [SP, C.c_char_p, C.c_int]
+    lib.ns_spectral_energy_spectrum.argtypes = [SP, C.c_int, c_double_p, C.POINTER(C.c_int)]
+    lib.ns_spectral_save_state.argtypes = [SP, C.POINTER(orc.ForcingState), C.c_char_p]
+    lib.ns_spectral_load_state.argtypes = [SP, C.POINTER(orc.ForcingState), C.c_char_p]
     lib.ns_forcing_config_default.restype = None
     lib.ns_forcing_config_default.argtypes = [C.POINTER(orc.ForcingConfig)]
     lib.ns_forcing_state_init.argtypes = [C.POINTER(orc.ForcingState), C.POINTER(orc.ForcingConfig), c_double_p,

@@ -154,6 +154,102 @@ def _lazy_run_steps(lib, orc_mod, kind):
     o.close()
 
 
+def _forced_solver(lib, kind, nx=64, ny=32, sfd=False):
+    """solver + forcing state of the forced test case (random-phase IC, hyperviscosity, band [0.5, 4])"""
+    s = hostlib.Solver(lib, nx, ny, Re=750.0)
+    lib.ns_spectral_initialize_random_phase(s.sp, 11, 8.0, 5.0)
+    h = orc.Hyperviscosity()
+    lib.ns_spectral_hyperviscosity_default(C.byref(h))
+    h.enabled, h.coefficient, h.order, h.cutoff_ratio = 1, 0.5, 4, 0.3
+    if sfd:
+        h.sfd_enabled, h.sfd_strength, h.sfd_timescale = 1, 0.2, 0.05
+    lib.ns_spectral_hyperviscosity_set(s.sp, C.byref(h))
+    cfg = orc.ForcingConfig()
+    lib.ns_forcing_config_default(C.byref(cfg))
+    cfg.kmin, cfg.kmax, cfg.energy_target, cfg.correlation_time, cfg.seed = 0.5, 4.0, 1.25, 0.4, 42
+    cfg.type = 1 if kind == "colored" else 0
+    fs = orc.ForcingState()
+    assert lib.ns_forcing_state_init(C.byref(fs), C.byref(cfg), s.s.k2, s.s.nkx, s.s.nky) == 0
+    return s, fs
+
+
+def _restart_bit_exact(lib, tmp_path, kind):
+    """4 steps, save, 5 more == load into a fresh solver, 5 steps, bit for bit
+    (omega_hat, SFD state, t, dt, forcing stream position, coloured-noise state)."""
+    path = str(tmp_path / ("restart_%s.bin" % kind)).encode()
+    a, fa = _forced_solver(lib, kind, sfd=True)
+    lib.ns_spectral_set_sync_policy(a.sp, 1)
+    assert lib.ns_spectral_run_steps(a.sp, 4, C.byref(fa)) == 0
+    assert lib.ns_spectral_save_state(a.sp, C.byref(fa), path) == 0, lib.ns_spectral_last_error()
+    assert lib.ns_spectral_run_steps(a.sp, 5, C.byref(fa)) == 0
+    lib.ns_spectral_sync_to_host(a.sp, 0xFFFF)
+
+    b, fb = _forced_solver(lib, kind, sfd=True)
+    b.arr("omega_hat")[...] = 0.0          # everything must come from the file
+    lib.ns_spectral_set_sync_policy(b.sp, 1)
+    assert lib.ns_spectral_load_state(b.sp, C.byref(fb), path) == 0, lib.ns_spectral_last_error()
+    assert lib.ns_spectral_run_steps(b.sp, 5, C.byref(fb)) == 0
+    lib.ns_spectral_sync_to_host(b.sp, 0xFFFF)
+    assert fb.rng_state == fa.rng_state and fb.have_spare == fa.have_spare
+    assert b.s.t == a.s.t and b.s.dt == a.s.dt
+    assert np.array_equal(b.arr("omega_hat"), a.arr("omega_hat"))
+    assert np.array_equal(b.arr("sfd_hat"), a.arr("sfd_hat"))
+    assert np.linalg.norm(a.arr("sfd_hat")) > 0
+
+    # error paths: wrong grid, not a restart file
+    c = hostlib.Solver(lib, 32, 32, Re=750.0)
+    assert lib.ns_spectral_load_state(c.sp, None, path) == -1
+    assert b"grid" in lib.ns_spectral_last_error()
+    junk = tmp_path / "junk.bin"
+    junk.write_bytes(b"not a restart file" * 10)
+    assert lib.ns_spectral_load_state(c.sp, None, str(junk).encode()) == -1
+    c.close()
+    for s_, f_ in ((a, fa), (b, fb)):
+        lib.ns_forcing_state_free(C.byref(f_))
+        s_.close()
+
+
+def _spectrum_and_strided_output(lib, tmp_path):
+    """device shell spectrum (LAZY) == host loop of spectral_analysis.c:103-142
+    (EAGER) == numpy; strided dump = every stride-th line of the reference-format dump."""
+    s, fs = _forced_solver(lib, "white", nx=64, ny=64)
+    lib.ns_spectral_compute_derivatives(s.sp)
+    nb = min(s.s.nkx, s.s.nky // 2)
+    ek_h, cnt_h = np.zeros(nb), np.zeros(nb, dtype=np.int32)
+    ek_d, cnt_d = np.zeros(nb), np.zeros(nb, dtype=np.int32)
+    ip = C.POINTER(C.c_int)
+    assert lib.ns_spectral_energy_spectrum(s.sp, nb, ek_h.ctypes.data_as(hostlib.c_double_p),
+                                           cnt_h.ctypes.data_as(ip)) == 0
+    lib.ns_spectral_set_sync_policy(s.sp, 1)
+    assert lib.ns_spectral_energy_spectrum(s.sp, nb, ek_d.ctypes.data_as(hostlib.c_double_p),
+                                           cnt_d.ctypes.data_as(ip)) == 0
+    k2 = np.ctypeslib.as_array(s.s.k2, shape=(s.s.nky * s.s.nkx,))
+    bins = (np.sqrt(k2) + 0.5).astype(np.int64)
+    e = 0.5 * (np.abs(s.arr("u_hat").ravel()) ** 2 + np.abs(s.arr("v_hat").ravel()) ** 2)
+    ok = bins < nb
+    ek_n = np.bincount(bins[ok], weights=e[ok], minlength=nb)
+    cnt_n = np.bincount(bins[ok], minlength=nb)
+    assert np.array_equal(cnt_h, cnt_n) and np.array_equal(cnt_d, cnt_n)
+    assert ek_n.max() > 0
+    assert np.max(np.abs(ek_h - ek_n)) <= 1e-13 * ek_n.max()
+    assert np.max(np.abs(ek_d - ek_n)) <= 1e-13 * ek_n.max()
+
+    full, thin = tmp_path / "full.dat", tmp_path / "thin.dat"
+    lib.ns_spectral_output_solution(s.sp, str(full).encode())
+    assert lib.ns_spectral_output_solution_strided(s.sp, str(thin).encode(), 4) == 0
+    assert lib.ns_spectral_output_solution_strided(s.sp, str(thin).encode(), 0) == -1
+    fl = full.read_text().split("\n")
+    assert fl[0] == "# Spectral Navier-Stokes Solution" and fl[1] == "# x y u v omega psi"
+    nx, ny = s.s.nx, s.s.ny
+    want = fl[:2]
+    for j in range(0, ny, 4):
+        row0 = 2 + j * (nx + 1)
+        want += fl[row0:row0 + nx:4] + [""]
+    assert thin.read_text().split("\n") == want + [""]
+    lib.ns_forcing_state_free(C.byref(fs))
+    s.close()
+
+
 def test_reference_unit_tests_emu(emu_host):
     _reference_unit_tests(emu_host)
 
@@ -165,6 +261,26 @@ def test_conservation_and_eager_parity_emu(emu_host, oracles):
 @pytest.mark.parametrize("kind", ["white", "colored"])
 def test_lazy_run_steps_emu(emu_host, oracles, kind):
     _lazy_run_steps(emu_host, oracles, kind)
+
+
+@pytest.mark.parametrize("kind", ["white", "colored"])
+def test_restart_bit_exact_emu(emu_host, tmp_path, kind):
+    _restart_bit_exact(emu_host, tmp_path, kind)
+
+
+def test_spectrum_and_strided_output_emu(emu_host, tmp_path):
+    _spectrum_and_strided_output(emu_host, tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["white", "colored"])
+def test_restart_bit_exact_gpu(gpu_host, tmp_path, kind):
+    _restart_bit_exact(gpu_host, tmp_path, kind)
+
+
+@pytest.mark.gpu
+def test_spectrum_and_strided_output_gpu(gpu_host, tmp_path):
+    _spectrum_and_strided_output(gpu_host, tmp_path)
 
 
 @pytest.mark.gpu
@@ -197,3 +313,24 @@ def test_cli_runs_with_config_files(cuda_lib, tmp_path):
     assert "Resolution: 128x64 modes" in out.stdout
     assert "=== SIMULATION COMPLETED ===" in out.stdout
     assert "Step 10:" in out.stdout
+
+
+@pytest.mark.gpu
+def test_cli_restart_resumes_bit_exact(cuda_lib, tmp_path):
+    """restart.save / restart.load: 20 forced steps in one run == 10 + save, load + 10 (same final
+    energy and enstrophy lines, printed with 7 significant digits, and the same final time)."""
+    exe = os.path.join(ROOT, "navier-stokes-solvers_b200", "bin", "ns_spectral_solver")
+    base = ("[grid]\nnx = 64\nny = 64\n[fluid]\nRe = 500.0\n[time]\nt_end = 100.0\nmax_steps = %d\n"
+            "[init]\ntype = random_phase\n[forcing]\ntype = colored\nenergy_target = 0.5\nseed = 9\n"
+            "[output]\ninterval = 0\n[restart]\n%s\n")
+    def run(name, steps, restart):
+        f = tmp_path / name
+        f.write_text(base % (steps, restart))
+        out = subprocess.run([exe, "--config", str(f)], capture_output=True, text=True, cwd=tmp_path, timeout=300)
+        assert out.returncode == 0, out.stderr
+        return [l for l in out.stdout.split("\n") if l.startswith(("Final time", "Final energy", "Final enstrophy"))]
+    whole = run("whole.ini", 20, "save = whole.bin")
+    run("first.ini", 10, "save = half.bin")
+    second = run("second.ini", 10, "load = half.bin\nsave = second.bin")
+    assert len(whole) == 3 and whole == second
+    assert (tmp_path / "whole.bin").read_bytes() == (tmp_path / "second.bin").read_bytes()
