@@ -97,6 +97,7 @@ def load_nsb(path=None):
         "nsb_mgpu_link_local": [C.POINTER(C.c_void_p), C.c_int],
         "nsb_mgpu_group_step": [C.POINTER(C.c_void_p), C.c_int, C.c_double],
         "nsb_spectral_stats": [C.c_void_p, c_double_p],
+        "nsb_energy_spectrum": [C.c_void_p, C.c_int, c_double_p, C.POINTER(C.c_int)],
         "nsb_mgpu_group_gather": [C.POINTER(C.c_void_p), C.c_int],
         "nsb_mgpu_group_scatter": [C.POINTER(C.c_void_p), C.c_int],
     }
@@ -237,6 +238,12 @@ class NsbContext:
         out = (C.c_double * 6)()
         self._ck(self.lib.nsb_spectral_stats(self.h, out))
         return dict(zip(["total", "high_k", "max_abs", "tail", "tail_modes", "k2_last"], out[:]))
+
+    def energy_spectrum(self, nbins):
+        """shell sums of 0.5 (|u_hat|^2 + |v_hat|^2) and mode counts (spectral_analysis.c:103-142)"""
+        ek, cnt = (C.c_double * nbins)(), (C.c_int * nbins)()
+        self._ck(self.lib.nsb_energy_spectrum(self.h, nbins, ek, cnt))
+        return np.array(ek[:]), np.array(cnt[:])
 
     def state(self):
         dt, t, st = C.c_double(), C.c_double(), C.c_int()

@@ -143,4 +143,17 @@ def check_spectral_stats(nsb, lib, nx, ny, **plan):
     assert abs(st["max_abs"] - mag.max()) <= 1e-14 * mag.max()
     assert abs(st["tail"] - (mag[k2 > 0.25 * k2_last] ** 2).sum()) <= 1e-12 * (mag ** 2).sum()
     assert st["tail_modes"] == float((k2 > 0.25 * k2_last).sum())
+    # nsb_energy_spectrum against numpy (spectral_analysis.c:103-142 over spectral_core.c:8-34)
+    nb = min(nx // 2 + 1, ny // 2)
+    ek, cnt = c.energy_spectrum(nb)
+    kx = (2.0 * np.pi * np.arange(nx // 2 + 1) / c.Lx)[None, :]
+    jj = np.arange(ny)
+    ky = np.where(jj <= ny // 2, 2.0 * np.pi * jj / c.Ly, 2.0 * np.pi * (jj - ny) / c.Ly)[:, None]
+    psi = np.where(k2 > 1e-12, -w / np.where(k2 > 1e-12, k2, 1.0), 0.0)
+    e = 0.5 * (np.abs(ky * psi) ** 2 + np.abs(kx * psi) ** 2)
+    bins = (np.sqrt(k2) + 0.5).astype(np.int64)
+    ok = bins < nb
+    assert np.array_equal(cnt, np.bincount(bins[ok], minlength=nb))
+    want = np.bincount(bins[ok], weights=e[ok], minlength=nb)
+    assert np.max(np.abs(ek - want)) <= 1e-12 * want.max()
     c.close()

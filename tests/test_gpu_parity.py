@@ -93,6 +93,45 @@ def test_large_size_properties_16384(nsb, cuda_lib):
     c.close()
 
 
+def test_large_size_properties_32768(nsb, cuda_lib):
+    """BASELINE config 5's grid (32768^2, 8.6 GB per spectral array) on ONE B200: the generic kernels
+    (Y1 = X2 = 2048, 16-point short factors) hold it in about 100 GB of the 180 GB. Same size-independent
+    properties as at 16384^2; no oracle (148 GB on the CPU)."""
+    import psutil
+    if psutil.virtual_memory().available < 48 * 2**30:
+        pytest.skip("needs ~35 GB of host memory for the upload / download copies")
+    n = 32768
+    c = nsb.NsbContext(n, n, Re=100.0, lib=cuda_lib)
+    assert c.plan()["Y1"] * c.plan()["Y2"] == n
+    rng = np.random.default_rng(5)
+    nkx = n // 2 + 1
+    w = np.zeros((n, nkx), dtype=np.complex128)
+    kk = 64
+    blk = rng.standard_normal((2 * kk + 1, kk + 1)) + 1j * rng.standard_normal((2 * kk + 1, kk + 1))
+    rows = np.arange(-kk, kk + 1) % n
+    w[rows[:, None], np.arange(kk + 1)[None, :]] = blk
+    w[0, 0] = 0.0
+    col = w[:, 0].copy()
+    w[:, 0] = 0.5 * (col + np.conj(col[(-np.arange(n)) % n]))
+    c.upload(nsb.OMEGA_HAT, w)
+    c.spectral_to_physical([nsb.OMEGA_HAT], [nsb.OMEGA])
+    c.physical_to_spectral(nsb.OMEGA, nsb.SCRATCH_HAT)
+    back = c.download(nsb.SCRATCH_HAT)
+    sub = back[rows[:, None], np.arange(kk + 1)[None, :]]
+    ref = w[rows[:, None], np.arange(kk + 1)[None, :]]
+    assert pc.rel(sub, ref) < 1e-13
+    back[rows[:, None], np.arange(kk + 1)[None, :]] = 0.0
+    assert not back.any()                     # nothing leaked outside the block
+    del back, w
+    d0 = c.diagnostics()
+    for _ in range(2):
+        c.step(0.0)
+    d1 = c.diagnostics()
+    assert 0 < d1["energy"] < d0["energy"]
+    assert 0 < d1["enstrophy"] < d0["enstrophy"]
+    c.close()
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("n,steps", [(2048, 3), (4096, 2)])
 def test_step_chain_modes(nsb, cuda_lib, oracles, monkeypatch, mode, n, steps):
