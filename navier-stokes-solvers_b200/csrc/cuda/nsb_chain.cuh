@@ -13,7 +13,7 @@
  *   F  (was k_beta_fwd)   split of the packed forward spectrum, x twiddle, length-X1 DFT,
  *                         length-Y2 DFT -> T'
  *
- * The work unit is a SLAB of 16 y rows (GY = 16/Y2 consecutive y1 values): B produces the
+ * The work unit is a SLAB of R = 16 y rows (32 when Y2 == 32; GY = R/Y2 consecutive y1 values): B produces the
  * 16*X1 combs of a slab at once, G consumes them pair by pair, F needs all of them.
  *
  * Two ways to run it:
@@ -33,7 +33,8 @@
 
 #include "nsb_kernels.cuh"
 
-#define NSB_CH_ROWS 16
+#define NSB_CH_ROWS 16     /* rows of a slab when Y2 <= 16 */
+#define NSB_CH_ROWS_MAX 32 /* Y2 == 32 (32768 rows): one y1 value per slab */
 
 struct ChainArgs {
     const cd *T; /* alpha output, 4 fields x rowsT own rows (pitch PT) */
@@ -46,8 +47,9 @@ struct ChainArgs {
     int nslab;   /* slabs of this launch */
     int slab0;   /* first slab of this launch (slab ranges run concurrently on two streams) */
     int nslotZ, nslotP;
-    int GY;      /* y1 values per slab = 16 / Y2 */
-    int NQ;      /* combs per slab = 16 * X1 */
+    int R;       /* y rows per slab: a.R, or a.R_MAX when Y2 == 32 */
+    int GY;      /* y1 values per slab = R / Y2 */
+    int NQ;      /* combs per slab = R * X1 */
     int nbatch;  /* k2 batches */
     int nd, nm;  /* direct / mirror column segments (nsb_beta_segs) */
     unsigned long long *umax_bits;
@@ -84,7 +86,7 @@ __device__ __forceinline__ void chain_B_step1(const NsbGeom &g, const ChainArgs 
         }
 #pragma unroll
         for (int y2 = 0; y2 < Y2; ++y2)
-            tile[(size_t)((fi * NSB_CH_ROWS + gy * Y2 + y2) * nseg + seg) * g.BC + cc] = x[y2];
+            tile[(size_t)((fi * a.R + gy * Y2 + y2) * nseg + seg) * g.BC + cc] = x[y2];
     }
 }
 
@@ -106,13 +108,13 @@ template <int X1>
 __device__ __forceinline__ void chain_B_step2(const NsbGeom &g, const ChainArgs &a, const cd *tile, int slot, int pp,
                                               int kb) {
     const int nseg = a.nd + a.nm;
-    for (int w = threadIdx.x; w < NSB_CH_ROWS * g.BC; w += blockDim.x) {
+    for (int w = threadIdx.x; w < a.R * g.BC; w += blockDim.x) {
         const int r = w / g.BC, cc = w - r * g.BC;
         const int k2 = kb + cc;
         if (k2 > g.X2h) continue;
         cd A[X1], B[X1];
         chain_gather<X1>(A, tile, r, nseg, a.nd, a.nm, g.BC, cc);
-        chain_gather<X1>(B, tile, NSB_CH_ROWS + r, nseg, a.nd, a.nm, g.BC, cc);
+        chain_gather<X1>(B, tile, a.R + r, nseg, a.nd, a.nm, g.BC, cc);
         if (k2 == 0) { /* FFTW c2r ignores Im of the kx = 0 bin */
             A[0].y = 0.0;
             B[0].y = 0.0;
@@ -149,7 +151,8 @@ __device__ __forceinline__ void chain_B_item(const NsbGeom &g, const ChainArgs &
         case 2: chain_B_step1<2>(g, a, tile, slab, pp, kb); break;
         case 4: chain_B_step1<4>(g, a, tile, slab, pp, kb); break;
         case 8: chain_B_step1<8>(g, a, tile, slab, pp, kb); break;
-        default: chain_B_step1<16>(g, a, tile, slab, pp, kb); break;
+        case 16: chain_B_step1<16>(g, a, tile, slab, pp, kb); break;
+        default: chain_B_step1<32>(g, a, tile, slab, pp, kb); break;
     }
     __syncthreads();
     switch (g.X1) {
@@ -157,7 +160,8 @@ __device__ __forceinline__ void chain_B_item(const NsbGeom &g, const ChainArgs &
         case 2: chain_B_step2<2>(g, a, tile, slot, pp, kb); break;
         case 4: chain_B_step2<4>(g, a, tile, slot, pp, kb); break;
         case 8: chain_B_step2<8>(g, a, tile, slot, pp, kb); break;
-        default: chain_B_step2<16>(g, a, tile, slot, pp, kb); break;
+        case 16: chain_B_step2<16>(g, a, tile, slot, pp, kb); break;
+        default: chain_B_step2<32>(g, a, tile, slot, pp, kb); break;
     }
 }
 
@@ -247,7 +251,7 @@ __device__ __forceinline__ void chain_F_step1(const NsbGeom &g, const ChainArgs 
                                               const cd *twtab) {
     const int nseg = a.nd + a.nm;
     const int NP = a.NQ >> 1;
-    for (int w = threadIdx.x; w < NSB_CH_ROWS * g.BC; w += blockDim.x) {
+    for (int w = threadIdx.x; w < a.R * g.BC; w += blockDim.x) {
         const int r = w / g.BC, cc = w - r * g.BC;
         const int k2 = kb + cc;
         cd x[X1];
@@ -319,7 +323,8 @@ __device__ __forceinline__ void chain_F_item(const NsbGeom &g, const ChainArgs &
         case 2: chain_F_step1<2>(g, a, tile, slot, kb, twtab); break;
         case 4: chain_F_step1<4>(g, a, tile, slot, kb, twtab); break;
         case 8: chain_F_step1<8>(g, a, tile, slot, kb, twtab); break;
-        default: chain_F_step1<16>(g, a, tile, slot, kb, twtab); break;
+        case 16: chain_F_step1<16>(g, a, tile, slot, kb, twtab); break;
+        default: chain_F_step1<32>(g, a, tile, slot, kb, twtab); break;
     }
     __syncthreads();
     switch (g.Y2) {
@@ -327,12 +332,13 @@ __device__ __forceinline__ void chain_F_item(const NsbGeom &g, const ChainArgs &
         case 2: chain_F_step2<2>(g, a, tile, slab, kb); break;
         case 4: chain_F_step2<4>(g, a, tile, slab, kb); break;
         case 8: chain_F_step2<8>(g, a, tile, slab, kb); break;
-        default: chain_F_step2<16>(g, a, tile, slab, kb); break;
+        case 16: chain_F_step2<16>(g, a, tile, slab, kb); break;
+        default: chain_F_step2<32>(g, a, tile, slab, kb); break;
     }
 }
 
 /* ------------------------------------------------ B, TMA-fed and persistent */
-/* requires NSB_CH_ROWS*BC*16 bytes per box row block, i.e. BC*2 doubles <= 256 and 16 rows */
+/* requires R*BC*16 bytes per box row block, i.e. BC*2 doubles <= 256 and R <= 256 rows */
 
 /*
  * Valid part of column segment `seg` for the k2 batch starting at kb, in ASCENDING memory
@@ -372,15 +378,15 @@ __device__ __forceinline__ void chain_B_issue(const NsbGeom &g, const ChainArgs 
     const int nseg = a.nd + a.nm;
     if (threadIdx.x == 0) {
         nsb_fence_proxy_async();
-        nsb_mbar_expect_tx(bar, (unsigned)(2 * nseg) * (unsigned)(NSB_CH_ROWS * g.BC * 16));
+        nsb_mbar_expect_tx(bar, (unsigned)(2 * nseg) * (unsigned)(a.R * g.BC * 16));
     }
     __syncthreads();
     if ((int)threadIdx.x < 2 * nseg) {
         const int fi = threadIdx.x / nseg, seg = threadIdx.x - fi * nseg;
         const int f = pp == 0 ? (fi ? 3 : 0) : (fi ? 2 : 1);
         const int col0 = (seg < a.nd) ? seg * g.X2 + kb : (seg - a.nd) * g.X2 + g.X2 - kb - (g.BC - 1);
-        nsb_tma_2d_g2s(tile + (size_t)(fi * nseg + seg) * NSB_CH_ROWS * g.BC, tmT, 2 * col0,
-                       f * a.rowsT + slab * NSB_CH_ROWS, bar);
+        nsb_tma_2d_g2s(tile + (size_t)(fi * nseg + seg) * a.R * g.BC, tmT, 2 * col0,
+                       f * a.rowsT + slab * a.R, bar);
     }
 }
 
@@ -397,7 +403,7 @@ __device__ __forceinline__ void chain_B2_step1(const NsbGeom &g, const ChainArgs
         const int seg = r / g.BC, pos = r - seg * g.BC;
         int p0, cnt, c0;
         chain_seg_range(g, a.nd, seg, kb, &p0, &cnt, &c0);
-        cd *col = tile + (size_t)((fi * nseg + seg) * NSB_CH_ROWS + gy * Y2) * g.BC + pos;
+        cd *col = tile + (size_t)((fi * nseg + seg) * a.R + gy * Y2) * g.BC + pos;
         cd x[Y2];
         if (pos >= p0 && pos < p0 + cnt) {
 #pragma unroll
@@ -415,14 +421,14 @@ __device__ __forceinline__ void chain_B2_step1(const NsbGeom &g, const ChainArgs
 /* gather for tiles in memory order (mirror segments reversed) */
 template <int X1>
 __device__ __forceinline__ void chain_gather_mo(cd (&x)[X1], const cd *tile, int fi, int r, int nseg, int nd, int nm,
-                                                int BC, int cc) {
+                                                int BC, int cc, int R) {
 #pragma unroll
     for (int k1 = 0; k1 < X1; ++k1) {
         if (X1 == 1 || k1 < X1 / 2) {
-            x[k1] = (k1 < nd) ? tile[(size_t)((fi * nseg + k1) * NSB_CH_ROWS + r) * BC + cc] : cmk(0.0, 0.0);
+            x[k1] = (k1 < nd) ? tile[(size_t)((fi * nseg + k1) * R + r) * BC + cc] : cmk(0.0, 0.0);
         } else {
             const int kp = X1 - 1 - k1;
-            x[k1] = (kp < nm) ? cconj(tile[(size_t)((fi * nseg + nd + kp) * NSB_CH_ROWS + r) * BC + (BC - 1 - cc)])
+            x[k1] = (kp < nm) ? cconj(tile[(size_t)((fi * nseg + nd + kp) * R + r) * BC + (BC - 1 - cc)])
                               : cmk(0.0, 0.0);
         }
     }
@@ -436,17 +442,17 @@ template <int X1, bool MO>
 __device__ __forceinline__ void chain_B_step2x(const NsbGeom &g, const ChainArgs &a, const cd *tile, int slot, int pp,
                                                int kb, const cd *twtab) {
     const int nseg = a.nd + a.nm;
-    for (int w = threadIdx.x; w < NSB_CH_ROWS * g.BC; w += blockDim.x) {
+    for (int w = threadIdx.x; w < a.R * g.BC; w += blockDim.x) {
         const int r = w / g.BC, cc = w - r * g.BC;
         const int k2 = kb + cc;
         if (k2 > g.X2h) continue;
         cd A[X1], B[X1];
         if (MO) {
-            chain_gather_mo<X1>(A, tile, 0, r, nseg, a.nd, a.nm, g.BC, cc);
-            chain_gather_mo<X1>(B, tile, 1, r, nseg, a.nd, a.nm, g.BC, cc);
+            chain_gather_mo<X1>(A, tile, 0, r, nseg, a.nd, a.nm, g.BC, cc, a.R);
+            chain_gather_mo<X1>(B, tile, 1, r, nseg, a.nd, a.nm, g.BC, cc, a.R);
         } else {
             chain_gather<X1>(A, tile, r, nseg, a.nd, a.nm, g.BC, cc);
-            chain_gather<X1>(B, tile, NSB_CH_ROWS + r, nseg, a.nd, a.nm, g.BC, cc);
+            chain_gather<X1>(B, tile, a.R + r, nseg, a.nd, a.nm, g.BC, cc);
         }
         if (k2 == 0) { /* FFTW c2r ignores Im of the kx = 0 bin */
             A[0].y = 0.0;
@@ -489,7 +495,7 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
      * LDS/STS instead of the generic LD/ST this cast produces, made the kernel 7 % SLOWER.) */
     cd *smem = reinterpret_cast<cd *>((reinterpret_cast<size_t>(smem_raw) + 127) & ~(size_t)127);
     const int nseg = a.nd + a.nm;
-    const size_t tile_elems = (size_t)2 * NSB_CH_ROWS * nseg * g.BC;
+    const size_t tile_elems = (size_t)2 * a.R * nseg * g.BC;
     nsb_mbar_t *bars = reinterpret_cast<nsb_mbar_t *>(smem + 2 * tile_elems);
     cd *twtab = smem + 2 * tile_elems + 4; /* BC * X1 x twiddles of the current batch */
     if (threadIdx.x == 0) {
@@ -527,7 +533,8 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
             case 2: chain_B2_step1<2>(g, a, tile, kb); break;
             case 4: chain_B2_step1<4>(g, a, tile, kb); break;
             case 8: chain_B2_step1<8>(g, a, tile, kb); break;
-            default: chain_B2_step1<16>(g, a, tile, kb); break;
+            case 16: chain_B2_step1<16>(g, a, tile, kb); break;
+            default: chain_B2_step1<32>(g, a, tile, kb); break;
         }
         __syncthreads();
         const int slot = slab % a.nslotZ;
@@ -536,7 +543,8 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
             case 2: chain_B_step2x<2, true>(g, a, tile, slot, pp, kb, twtab); break;
             case 4: chain_B_step2x<4, true>(g, a, tile, slot, pp, kb, twtab); break;
             case 8: chain_B_step2x<8, true>(g, a, tile, slot, pp, kb, twtab); break;
-            default: chain_B_step2x<16, true>(g, a, tile, slot, pp, kb, twtab); break;
+            case 16: chain_B_step2x<16, true>(g, a, tile, slot, pp, kb, twtab); break;
+            default: chain_B_step2x<32, true>(g, a, tile, slot, pp, kb, twtab); break;
         }
         __syncthreads(); /* the tile is free for the copies of item n+2 */
     }

@@ -75,6 +75,7 @@ struct nsb_ctx {
     int k_truth; /* 1: kW0 (and kSFD) hold the current state, the reference-layout fields are stale */
     /* chain (nsb_chain.cuh): 0 off, 1 three plain kernels, 2 persistent dataflow kernel */
     int chain_mode;
+    int ch_rows; /* y rows per chain slab (ChainArgs::R) */
     cd *chZ, *chP;     /* L2-resident rings of the persistent kernel */
     unsigned *chCtr;   /* ticket + per-slab completion counters */
     int ch_slotZ, ch_slotP, ch_leadG, ch_leadF, ch_ctas, ch_btma;
@@ -222,16 +223,17 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->N = (size_t)g.nx * g.ny;
     c->M = (size_t)g.nkx * g.ny;
     /* factorisation */
-    int Y1 = p->y1 > 0 ? p->y1 : (g.ny <= 1024 ? g.ny : (g.ny / 16 > 1024 ? g.ny / 16 : 1024));
-    int X2 = p->x2 > 0 ? p->x2 : (g.nx <= 1024 ? g.nx : (g.nx / 16 > 1024 ? g.nx / 16 : 1024));
+    /* long factors of 1024 (the warp-resident transforms) with short factors up to 32: 32768 = 1024 x 32 */
+    int Y1 = p->y1 > 0 ? p->y1 : (g.ny <= 1024 ? g.ny : (g.ny / 32 > 1024 ? g.ny / 32 : 1024));
+    int X2 = p->x2 > 0 ? p->x2 : (g.nx <= 1024 ? g.nx : (g.nx / 32 > 1024 ? g.nx / 32 : 1024));
     if (!pow2(Y1) || Y1 > g.ny || Y1 < 2 || !pow2(X2) || X2 > g.nx || X2 < 2) {
         delete c->smem_set; delete c;
         return fail("bad factorisation y1=%d x2=%d", Y1, X2);
     }
     g.Y1 = Y1; g.Y2 = g.ny / Y1; g.X2 = X2; g.X1 = g.nx / X2; g.X2h = X2 / 2;
-    if (g.Y2 > 16 || g.X1 > 16) {
+    if (g.Y2 > 32 || g.X1 > 32) {
         delete c->smem_set; delete c;
-        return fail("factorisation needs Y2=%d, X1=%d (max 16 each)", g.Y2, g.X1);
+        return fail("factorisation needs Y2=%d, X1=%d (max 32 each)", g.Y2, g.X1);
     }
     g.imax = (2 * g.nkx) / 3;  /* spectral_initialization.c:46 */
     g.ncol = g.imax + 1;
@@ -254,9 +256,12 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->tmT8_ok = 0;
     c->chCtr = nullptr;
     c->chain_mode = 0;
-    if (c->fast && g.X2 == 1024 && c->has_beta && g.ny % NSB_CH_ROWS == 0 && g.Y2 <= NSB_CH_ROWS &&
-        g.Y1 % (NSB_CH_ROWS / g.Y2) == 0) {
+    c->ch_rows = g.Y2 > NSB_CH_ROWS ? NSB_CH_ROWS_MAX : NSB_CH_ROWS;
+    if (c->fast && g.X2 == 1024 && c->has_beta && g.ny % c->ch_rows == 0 && g.Y2 <= c->ch_rows &&
+        g.Y1 % (c->ch_rows / g.Y2) == 0) {
         c->chain_mode = getenv("NSB_CHAIN") ? atoi(getenv("NSB_CHAIN")) : 1;
+        /* the persistent dataflow kernel keeps a whole 16-column B tile per CTA: 16-point factors only */
+        if (c->chain_mode == 2 && (g.Y2 > 16 || g.X1 > 16)) c->chain_mode = 1;
     }
     auto env_int = [](const char *name, int dflt) { return getenv(name) ? atoi(getenv(name)) : dflt; };
     c->ch_slotZ = env_int("NSB_CHAIN_SLOTS_Z", 8);
@@ -721,6 +726,7 @@ static int launch_beta_x(nsb_ctx *c, bool inverse, const BetaArgs &a) {
         case 4: return launch_beta_t<Y2, 4>(c, inverse, a);
         case 8: return launch_beta_t<Y2, 8>(c, inverse, a);
         case 16: return launch_beta_t<Y2, 16>(c, inverse, a);
+        case 32: return launch_beta_t<Y2, 32>(c, inverse, a);
     }
     return fail("unsupported X1=%d", c->g.X1);
 }
@@ -732,6 +738,7 @@ static int launch_beta(nsb_ctx *c, bool inverse, const BetaArgs &a) {
         case 4: return launch_beta_x<4>(c, inverse, a);
         case 8: return launch_beta_x<8>(c, inverse, a);
         case 16: return launch_beta_x<16>(c, inverse, a);
+        case 32: return launch_beta_x<32>(c, inverse, a);
     }
     return fail("unsupported Y2=%d", c->g.Y2);
 }
@@ -916,15 +923,17 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
     a.ybase = c->mg_rank * c->mg_rows;
     for (int p = 0; p < NSB_MAXP; ++p) a.Tpp[p] = c->mg_Tp[p < c->mg_world ? p : 0];
     a.cb = c->mg_cb;
-    a.nslab = c->mg_rows / NSB_CH_ROWS;
-    a.GY = NSB_CH_ROWS / g.Y2;
-    a.NQ = NSB_CH_ROWS * g.X1;
+    const int R = c->ch_rows;
+    a.R = R;
+    a.nslab = c->mg_rows / R;
+    a.GY = R / g.Y2;
+    a.NQ = R * g.X1;
     a.nbatch = (g.X2h + 1 + g.BC - 1) / g.BC; /* every k2 of a comb spectrum is written, also when X1 == 1 */
     nsb_beta_segs(g.imax, g.X1, g.X2, &a.nd, &a.nm);
     a.umax_bits = &c->d_sc->umax_bits;
     const int NP = a.NQ / 2;
     const int W = (c->chain_mode == 2 && c->ch_ctas == 2) ? (want_umax ? 3 : 4) : (want_umax ? 6 : 8);
-    const size_t tileB = (size_t)2 * NSB_CH_ROWS * (a.nd + a.nm) * g.BC * sizeof(cd);
+    const size_t tileB = (size_t)2 * R * (a.nd + a.nm) * g.BC * sizeof(cd);
     const size_t twtab = (size_t)g.BC * g.X1 * sizeof(cd);
     const size_t tileF = tileB / 2 + twtab;
     const size_t smemG = NSB_CH_TW_BYTES + (size_t)W * (want_umax ? NSB_CHG_WARP_BYTES(1) : NSB_CHG_WARP_BYTES(0));
@@ -952,28 +961,38 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
         }
         const int Wg = split ? (want_umax ? 3 : 4) : W;
         const size_t smemGp = NSB_CH_TW_BYTES + (size_t)Wg * (want_umax ? NSB_CHG_WARP_BYTES(1) : NSB_CHG_WARP_BYTES(0));
-        const bool use_tma = c->ch_btma && 2 * tileB + 64 + 128 + twtab <= 227 * 1024 && 2 * g.BC <= 256;
         /* measured: 8-column batches win while the tile is small (4096^2: 0.31 vs 0.40 ms), 16-column
          * batches with one 256-thread CTA per SM win at 16384^2 (3.56 vs 5.58 ms) when B runs alone */
-        const bool half = g.BC == 16 && (split || c->ch_bbc == 8 || (c->ch_bbc < 0 && tileB <= 48 * 1024));
+        bool half = g.BC == 16 && (split || c->ch_bbc == 8 || (c->ch_bbc < 0 && tileB <= 48 * 1024));
+        /* two tile stages must fit one SM: 32-point factors (32 rows x up to 22 segments per column) leave
+         * room for 8- or 4-column batches only; such CTAs are alone on their SM (256 threads) */
+        int bdiv = half ? 2 : 1;
+        const size_t smem_cap = 227 * 1024;
+        while (g.BC / bdiv > 4 && 2 * (tileB / bdiv) + 64 + 128 + twtab / bdiv > smem_cap) bdiv *= 2;
+        const bool narrow = bdiv > 1;
+        const bool two_ctas = half && bdiv == 2 && 2 * (2 * (tileB / 2) + 64 + 128 + twtab / 2 + 1024) <= smem_cap;
+        half = narrow;
+        const bool use_tma = c->ch_btma && 2 * (tileB / bdiv) + 64 + 128 + twtab / bdiv <= smem_cap && 2 * g.BC <= 256;
+        if (!use_tma && tileB > smem_cap)
+            return fail("the chain's B tile (%zu bytes) needs the TMA-fed kernel at this size (NSB_CHAIN_BTMA=1)", tileB);
         NsbGeom gB = g;
         ChainArgs aB = a;
-        if (use_tma && half) {
-            gB.BC = 8;
-            aB.nbatch = (g.X2h + 1 + 7) / 8;
+        if (use_tma && narrow) {
+            gB.BC = g.BC / bdiv;
+            aB.nbatch = (g.X2h + 1 + gB.BC - 1) / gB.BC;
         }
         nsb_tmap *tm = half ? &c->tmT8 : &c->tmT;
         if (use_tma) {
             int *tm_ok = half ? &c->tmT8_ok : &c->tmT_ok;
             if (!*tm_ok) {
                 if (make_tmap_2d(tm, c->bufA, (size_t)2 * g.PT, (size_t)4 * c->mg_rows, (size_t)g.PT * sizeof(cd),
-                                 2 * gB.BC, NSB_CH_ROWS))
+                                 2 * gB.BC, R))
                     return -1;
                 *tm_ok = 1;
             }
         }
-        const size_t tB = half ? tileB / 2 : tileB;
-        const size_t smemB = 2 * tB + 64 + 128 + (half ? twtab / 2 : twtab);
+        const size_t tB = tileB / bdiv;
+        const size_t smemB = 2 * tB + 64 + 128 + twtab / bdiv;
         if (split) {
             CK(cudaEventRecord(c->ch_ev[0], c->stream)); /* everything before the chain (alpha, barrier) */
             CK(cudaStreamWaitEvent(c->stream2, c->ch_ev[0], 0));
@@ -987,7 +1006,7 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
             if (split && pc > 0) CK(cudaStreamWaitEvent(st, c->ch_ev[1 + ((pc - 1) & 1)], 0));
             if (use_tma) {
                 prof_pre(c, PK_BETA_INV);
-                if (half) {
+                if (two_ctas) {
                     auto k = k_chain_B_tma<128, 2>;
                     if (ensure_smem(c, k, smemB, true)) return -1;
                     NSB_LAUNCH(k, dim3(2 * c->sm_count), dim3(128), smemB, st, gB, aB, *tm);
@@ -1660,7 +1679,7 @@ extern "C" int nsb_mgpu_setup(nsb_ctx *c, int rank, int world) {
     if (world > 1) {
         if (!(c->fast && g.Y1 == 1024 && c->chain_mode == 1))
             return fail("slab decomposition needs Y1 == X2 == 1024 with a beta split (grids 2048..16384) and NSB_CHAIN=1");
-        if ((g.ny / world) % NSB_CH_ROWS != 0) return fail("ny / world must be a multiple of %d", NSB_CH_ROWS);
+        if ((g.ny / world) % c->ch_rows != 0) return fail("ny / world must be a multiple of %d", c->ch_rows);
     }
     if (sync_ref(c)) return -1;
     CK(cudaStreamSynchronize(c->stream));

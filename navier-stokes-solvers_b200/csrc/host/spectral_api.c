@@ -866,13 +866,21 @@ int ns_spectral_save_state(NSSpectralData *d, const NSForcingState *fs, const ch
     memcpy(hd.magic, "NSBRST1", 8);
     hd.nx = d->nx; hd.ny = d->ny;
     hd.Lx = d->Lx; hd.Ly = d->Ly; hd.Re = d->Re; hd.t = d->t; hd.dt = d->dt; hd.cfl_factor = d->cfl_factor;
-    hd.hv = *h;
+    /* field by field: struct padding must not leak stack bytes into the file (identical states give
+     * identical files) */
+    hd.hv.enabled = h->enabled; hd.hv.coefficient = h->coefficient; hd.hv.order = h->order;
+    hd.hv.cutoff_ratio = h->cutoff_ratio; hd.hv.sfd_strength = h->sfd_strength;
+    hd.hv.sfd_timescale = h->sfd_timescale; hd.hv.sfd_enabled = h->sfd_enabled; hd.hv.kmax = h->kmax;
+    hd.hv.cutoff_wavenumber = h->cutoff_wavenumber; hd.hv.inv_bandwidth = h->inv_bandwidth;
     hd.has_sfd = sfd;
     if (fs) {
         if (fs->nkx != d->nkx || fs->nky != d->nky) { set_error("%s: forcing state does not match the grid", W); return -1; }
         hd.has_forcing = 1;
         hd.has_colored = (fs->config.type == NS_FORCING_COLORED_NOISE && fs->colored_state != NULL);
-        hd.fcfg = fs->config;
+        hd.fcfg.kmin = fs->config.kmin; hd.fcfg.kmax = fs->config.kmax;
+        hd.fcfg.energy_target = fs->config.energy_target;
+        hd.fcfg.correlation_time = fs->config.correlation_time;
+        hd.fcfg.seed = fs->config.seed; hd.fcfg.type = fs->config.type;
         hd.rng_state = fs->rng_state;
         hd.spare_gaussian = fs->spare_gaussian;
         hd.have_spare = fs->have_spare;

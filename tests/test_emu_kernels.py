@@ -87,6 +87,19 @@ def test_emu_chain(nsb, emu_lib, oracles, monkeypatch, mode, nx, ny, plan):
                       forcing=dict(kind="white"), **plan)
 
 
+@pytest.mark.parametrize("nx,ny,plan", [
+    (1024, 64, dict(x2=1024, y1=2)),           # X1 = 1, Y2 = 32: 32-row slabs, one y1 value each, 2 slabs
+    (2048, 64, dict(x2=1024, y1=2)),           # X1 = 2, Y2 = 32
+    (32768, 16, dict(x2=1024, y1=4)),          # X1 = 32, Y2 = 4: 22 column segments, 4-column B batches
+])
+def test_emu_chain_32_point_factors(nsb, emu_lib, oracles, nx, ny, plan):
+    """32768 = 1024 x 32: the chain with 32-point short factors (BASELINE config 5's factorisation),
+    plus the generic c2r / r2c kernels at the same factorisation (k_beta_*<32, .> / <., 32>)."""
+    pc.check_per_step(nsb, emu_lib, oracles, best_oracle_kind(oracles), nx, ny, 2, hv=HV,
+                      forcing=dict(kind="white"), **plan)
+    pc.check_transforms(nsb, emu_lib, oracles, best_oracle_kind(oracles), nx, ny, **plan)
+
+
 def test_emu_chain_ring_reuse(nsb, emu_lib, oracles, monkeypatch):
     """4 slabs through 2-slot rings: slot reuse and the completion-counter waits."""
     monkeypatch.setenv("NSB_CHAIN", "2")
