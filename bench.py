@@ -378,6 +378,10 @@ def run_gpu_arm(args):
                      "h2d_bytes_per_step": m_bytes + 2 * n_bytes, "d2h_bytes_per_step": 4 * m_bytes + 3 * n_bytes,
                      "api": "ns_spectral_compute_cfl_timestep + ns_spectral_advance_rk4, NS_SYNC_EAGER (pageable host arrays)"}
 
+    # fingerprint of the whole run: t and dt after all steps depend on max|u| over the whole field at every
+    # step, so runs with the same --warmup/--steps must agree bit for bit across GPU counts
+    fingerprint = {"t": float(s.s.t).hex(), "dt": float(s.s.dt).hex(), "t_dec": s.s.t, "dt_dec": s.s.dt,
+                   "steps_taken": args.warmup + args.steps + e2e_steps + prof_steps}
     host.ns_forcing_state_free(C.byref(fs))
     plan = (C.c_int * 8)()
     nsblib.nsb_get_plan(ctx, plan)
@@ -393,7 +397,7 @@ def run_gpu_arm(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"forced 2-D turbulence {n}x{n} FP64, hyperviscosity + white forcing, adaptive CFL "
-                                   f"dt (BASELINE config {'4' if n == 16384 else '3' if n == 4096 else 'n=' + str(n)})",
+                                   f"dt (BASELINE config {'4' if n == 16384 else '3' if n == 4096 else '5 grid, forced' if n == 32768 else 'n=' + str(n)})",
                        "Re": RE, "hyperviscosity": HV, "forcing": {"type": "white", **FORCING},
                        "init": "random-phase spectrum k^2 exp(-(k/8)^2), max|omega| = 5",
                        "parallelism": "1 GPU" if world == 1 else
@@ -403,7 +407,7 @@ def run_gpu_arm(args):
                        "l2": "inputs larger than L2: working set >> 126 MB at this size, no flush needed"
                              if n >= 2048 else "working set fits L2 at this size"},
             "clocks": clocks, "e2e": e2e, "e2e_eager": e2e_eager, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu}
+            "roofline": roofline, "cpu_baseline": cpu, "fingerprint": fingerprint}
     print(json.dumps(line), flush=True)
 
 

@@ -142,7 +142,9 @@ __device__ __forceinline__ void chain_B_step2(const NsbGeom &g, const ChainArgs 
     }
 }
 
-/* item = (slab, pp, batch); tile: 2 * 16 * nseg * BC complex. All threads call. */
+/* item = (slab, pp, batch); tile: 2 * R * nseg * BC complex. All threads call.
+ * BIG: also 32-point factors (kept out of the kernels for grids up to 16384: they would cost registers) */
+template <bool BIG>
 __device__ __forceinline__ void chain_B_item(const NsbGeom &g, const ChainArgs &a, cd *tile, int slab, int slot,
                                              int pp, int batch) {
     const int kb = batch * g.BC;
@@ -152,7 +154,9 @@ __device__ __forceinline__ void chain_B_item(const NsbGeom &g, const ChainArgs &
         case 4: chain_B_step1<4>(g, a, tile, slab, pp, kb); break;
         case 8: chain_B_step1<8>(g, a, tile, slab, pp, kb); break;
         case 16: chain_B_step1<16>(g, a, tile, slab, pp, kb); break;
-        default: chain_B_step1<32>(g, a, tile, slab, pp, kb); break;
+        default:
+            if constexpr (BIG) chain_B_step1<32>(g, a, tile, slab, pp, kb);
+            break;
     }
     __syncthreads();
     switch (g.X1) {
@@ -161,7 +165,9 @@ __device__ __forceinline__ void chain_B_item(const NsbGeom &g, const ChainArgs &
         case 4: chain_B_step2<4>(g, a, tile, slot, pp, kb); break;
         case 8: chain_B_step2<8>(g, a, tile, slot, pp, kb); break;
         case 16: chain_B_step2<16>(g, a, tile, slot, pp, kb); break;
-        default: chain_B_step2<32>(g, a, tile, slot, pp, kb); break;
+        default:
+            if constexpr (BIG) chain_B_step2<32>(g, a, tile, slot, pp, kb);
+            break;
     }
 }
 
@@ -311,7 +317,8 @@ __device__ __forceinline__ void chain_F_step2(const NsbGeom &g, const ChainArgs 
     }
 }
 
-/* item = (slab, batch); tile: 16 * nseg * BC complex. All threads call. */
+/* item = (slab, batch); tile: R * nseg * BC complex. All threads call. */
+template <bool BIG>
 __device__ __forceinline__ void chain_F_item(const NsbGeom &g, const ChainArgs &a, cd *tile, int slab, int slot,
                                              int batch) {
     const int kb = batch * g.BC;
@@ -324,7 +331,9 @@ __device__ __forceinline__ void chain_F_item(const NsbGeom &g, const ChainArgs &
         case 4: chain_F_step1<4>(g, a, tile, slot, kb, twtab); break;
         case 8: chain_F_step1<8>(g, a, tile, slot, kb, twtab); break;
         case 16: chain_F_step1<16>(g, a, tile, slot, kb, twtab); break;
-        default: chain_F_step1<32>(g, a, tile, slot, kb, twtab); break;
+        default:
+            if constexpr (BIG) chain_F_step1<32>(g, a, tile, slot, kb, twtab);
+            break;
     }
     __syncthreads();
     switch (g.Y2) {
@@ -333,7 +342,9 @@ __device__ __forceinline__ void chain_F_item(const NsbGeom &g, const ChainArgs &
         case 4: chain_F_step2<4>(g, a, tile, slab, kb); break;
         case 8: chain_F_step2<8>(g, a, tile, slab, kb); break;
         case 16: chain_F_step2<16>(g, a, tile, slab, kb); break;
-        default: chain_F_step2<32>(g, a, tile, slab, kb); break;
+        default:
+            if constexpr (BIG) chain_F_step2<32>(g, a, tile, slab, kb);
+            break;
     }
 }
 
@@ -482,13 +493,77 @@ __device__ __forceinline__ void chain_B_step2x(const NsbGeom &g, const ChainArgs
 }
 
 /*
+ * Step 2 for 32-point factors (X1 == 32), tiles in memory order. Two 32-point register DFTs per thread
+ * (A and B, as chain_B_step2x does) would need 256 registers for the data alone, and a 32-row x 4-column
+ * batch has only 128 (row, k2) items for 256 threads. The DFT is linear, so the packing moves IN FRONT of
+ * it: one thread transforms C = A + iB (-> Z[k2]), its neighbour D = A - iB (-> Z[1024-k2] = conj(D)):
+ * 256 items, one 32-point array each. At the two self-conjugate bins (k2 = 0 and 512) the stored value
+ * (Re a, Re b) needs both halves: ((C.x + D.x)/2, (C.y - D.y)/2), exchanged by one shuffle with lane^1.
+ * blockDim.x and 2*R*BC are multiples of 32, so a pair never straddles a warp and all lanes shuffle.
+ */
+template <int X1>
+__device__ __forceinline__ void chain_B_step2p(const NsbGeom &g, const ChainArgs &a, const cd *tile, int slot, int pp,
+                                               int kb, const cd *twtab) {
+    const int nseg = a.nd + a.nm;
+    const bool special_batch = (kb == 0) || (kb <= g.X2h && kb + g.BC > g.X2h);
+    for (int w = threadIdx.x; w < 2 * a.R * g.BC; w += blockDim.x) {
+        const int half = w & 1, item = w >> 1;
+        const int r = item / g.BC, cc = item - r * g.BC;
+        const int k2 = kb + cc;
+        const bool valid = k2 <= g.X2h;
+        const double sg = half ? -1.0 : 1.0;
+        cd x[X1];
+#pragma unroll
+        for (int k1 = 0; k1 < X1; ++k1) {
+            cd av, bv;
+            if (k1 < X1 / 2) {
+                if (k1 < a.nd) {
+                    av = tile[(size_t)((0 * nseg + k1) * a.R + r) * g.BC + cc];
+                    bv = tile[(size_t)((1 * nseg + k1) * a.R + r) * g.BC + cc];
+                } else {
+                    av = bv = cmk(0.0, 0.0);
+                }
+            } else {
+                const int kp = X1 - 1 - k1;
+                if (kp < a.nm) {
+                    av = cconj(tile[(size_t)((0 * nseg + a.nd + kp) * a.R + r) * g.BC + (g.BC - 1 - cc)]);
+                    bv = cconj(tile[(size_t)((1 * nseg + a.nd + kp) * a.R + r) * g.BC + (g.BC - 1 - cc)]);
+                } else {
+                    av = bv = cmk(0.0, 0.0);
+                }
+            }
+            if (k1 == 0 && k2 == 0) { /* FFTW c2r ignores Im of the kx = 0 bin */
+                av.y = 0.0;
+                bv.y = 0.0;
+            }
+            x[k1] = cmk(av.x - sg * bv.y, av.y + sg * bv.x); /* A + iB  |  A - iB */
+        }
+        nsb_dft<X1, true>(x);
+        cd *zo = a.Z + ((size_t)(slot * 2 + pp) * a.NQ + (size_t)r * X1) * 1024;
+        const bool special = (k2 == 0 || k2 == g.X2h);
+#pragma unroll
+        for (int x1 = 0; x1 < X1; ++x1) {
+            cd v = cmulc(x[x1], twtab[cc * X1 + x1]);
+            if (special_batch) { /* batch-uniform: every lane shuffles */
+                const double ox = __shfl_xor_sync(0xffffffffu, v.x, 1), oy = __shfl_xor_sync(0xffffffffu, v.y, 1);
+                if (special) v = cmk(0.5 * (v.x + ox), 0.5 * (v.y - oy)); /* half 0: (Re a, Re b) */
+            }
+            if (!valid) continue;
+            cd *row = zo + (size_t)x1 * 1024;
+            if (half == 0) row[k2] = v;
+            else if (!special) row[1024 - k2] = cmk(v.x, -v.y);
+        }
+    }
+}
+
+/*
  * Persistent, TMA-fed B: grid = SMs, each CTA walks items blockIdx.x + n*gridDim.x
  * (item = (slab, pp, batch), batch fastest). Two shared-memory stages: while the CTA
  * transforms the tile of item n, the bulk copies of item n+1 are in flight, so HBM latency
  * is off the critical path with one CTA per SM.
  * smem: 2 stages x (2*16*nseg*BC complex) + 2 mbarriers (+128 B alignment slack).
  */
-template <int NT, int MINB>
+template <int NT, int MINB, bool BIG>
 __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a, const NSB_GRID_CONSTANT nsb_tmap tmT) {
     NSB_DYN_SMEM(cd, smem_raw);
     /* 128-byte alignment for the TMA destination. (Measured: keeping shared-memory provenance, i.e.
@@ -534,7 +609,9 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
             case 4: chain_B2_step1<4>(g, a, tile, kb); break;
             case 8: chain_B2_step1<8>(g, a, tile, kb); break;
             case 16: chain_B2_step1<16>(g, a, tile, kb); break;
-            default: chain_B2_step1<32>(g, a, tile, kb); break;
+            default:
+                if constexpr (BIG) chain_B2_step1<32>(g, a, tile, kb);
+                break;
         }
         __syncthreads();
         const int slot = slab % a.nslotZ;
@@ -544,7 +621,9 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
             case 4: chain_B_step2x<4, true>(g, a, tile, slot, pp, kb, twtab); break;
             case 8: chain_B_step2x<8, true>(g, a, tile, slot, pp, kb, twtab); break;
             case 16: chain_B_step2x<16, true>(g, a, tile, slot, pp, kb, twtab); break;
-            default: chain_B_step2x<32, true>(g, a, tile, slot, pp, kb, twtab); break;
+            default:
+                if constexpr (BIG) chain_B_step2p<32>(g, a, tile, slot, pp, kb, twtab);
+                break;
         }
         __syncthreads(); /* the tile is free for the copies of item n+2 */
     }
@@ -553,9 +632,10 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
 /* ------------------------------------------------ the three plain kernels */
 
 /* grid (nbatch, 2, nslab) */
+template <bool BIG>
 __global__ void __launch_bounds__(256, 2) k_chain_B(NsbGeom g, ChainArgs a) {
     NSB_DYN_SMEM(cd, tile);
-    chain_B_item(g, a, tile, a.slab0 + blockIdx.z, (a.slab0 + blockIdx.z) % a.nslotZ, blockIdx.y, blockIdx.x);
+    chain_B_item<BIG>(g, a, tile, a.slab0 + blockIdx.z, (a.slab0 + blockIdx.z) % a.nslotZ, blockIdx.y, blockIdx.x);
 }
 
 /* grid (groups per slab, nslab), W warps */
@@ -606,9 +686,10 @@ __global__ void __launch_bounds__(256, 1) k_chain_Gp(NsbGeom g, ChainArgs a) {
 }
 
 /* grid (nbatch, nslab) */
+template <bool BIG>
 __global__ void __launch_bounds__(256) k_chain_F(NsbGeom g, ChainArgs a) {
     NSB_DYN_SMEM(cd, tile);
-    chain_F_item(g, a, tile, a.slab0 + blockIdx.y, (a.slab0 + blockIdx.y) % a.nslotP, blockIdx.x);
+    chain_F_item<BIG>(g, a, tile, a.slab0 + blockIdx.y, (a.slab0 + blockIdx.y) % a.nslotP, blockIdx.x);
 }
 
 /* ------------------------------------------------ the persistent dataflow kernel */
@@ -652,7 +733,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_chain(NsbGeom g, ChainArgs
             const int s = step - a.leadG - a.leadF;
             if (s >= 0 && s < a.nslab) {
                 chain_wait(&doneG[s], (unsigned)nG);
-                chain_F_item(g, a, tile, s, s % a.nslotP, idx);
+                chain_F_item<false>(g, a, tile, s, s % a.nslotP, idx);
                 chain_signal(&doneF[s]);
             }
         } else if (idx < nF + nG) { /* G of slab step - leadG */
@@ -668,7 +749,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_chain(NsbGeom g, ChainArgs
             if (s < a.nslab) {
                 if (s >= a.nslotZ) chain_wait(&doneG[s - a.nslotZ], (unsigned)nG);
                 idx -= nF + nG;
-                chain_B_item(g, a, tile, s, s % a.nslotZ, idx / a.nbatch, idx % a.nbatch);
+                chain_B_item<false>(g, a, tile, s, s % a.nslotZ, idx / a.nbatch, idx % a.nbatch);
                 chain_signal(&doneB[s]);
             }
         }

@@ -76,6 +76,7 @@ struct nsb_ctx {
     /* chain (nsb_chain.cuh): 0 off, 1 three plain kernels, 2 persistent dataflow kernel */
     int chain_mode;
     int ch_rows; /* y rows per chain slab (ChainArgs::R) */
+    int ch_fbc;  /* F batch width override (0 = automatic) */
     cd *chZ, *chP;     /* L2-resident rings of the persistent kernel */
     unsigned *chCtr;   /* ticket + per-slab completion counters */
     int ch_slotZ, ch_slotP, ch_leadG, ch_leadF, ch_ctas, ch_btma;
@@ -271,6 +272,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->ch_ctas = env_int("NSB_CHAIN_CTAS", 2) == 2 ? 2 : 1;
     c->ch_btma = env_int("NSB_CHAIN_BTMA", 1);
     c->ch_bbc = env_int("NSB_CHAIN_BBC", -1);
+    c->ch_fbc = env_int("NSB_CHAIN_FBC", 0);
     c->ch_pieces = env_int("NSB_CHAIN_PIECES", 0);         /* 0 = automatic */
     c->ch_gpersist = env_int("NSB_CHAIN_GPERSIST", 0); /* measured: the persistent G is 6 % slower (2.93 vs 2.77 ms) */
     c->alpha_cols = env_int("NSB_ALPHA_COLS", 4) == 8 ? 8 : 4;
@@ -924,6 +926,7 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
     for (int p = 0; p < NSB_MAXP; ++p) a.Tpp[p] = c->mg_Tp[p < c->mg_world ? p : 0];
     a.cb = c->mg_cb;
     const int R = c->ch_rows;
+    const bool big = g.Y2 > 16 || g.X1 > 16;
     a.R = R;
     a.nslab = c->mg_rows / R;
     a.GY = R / g.Y2;
@@ -935,7 +938,14 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
     const int W = (c->chain_mode == 2 && c->ch_ctas == 2) ? (want_umax ? 3 : 4) : (want_umax ? 6 : 8);
     const size_t tileB = (size_t)2 * R * (a.nd + a.nm) * g.BC * sizeof(cd);
     const size_t twtab = (size_t)g.BC * g.X1 * sizeof(cd);
-    const size_t tileF = tileB / 2 + twtab;
+    /* F keeps one tile per CTA; with 32-point factors a 16-column tile (180 KB) would leave one CTA per
+     * SM, so its batches narrow to 8 columns there (16384^2 and below: unchanged, 45 KB) */
+    int bcF = g.BC;
+    while (bcF > 4 && (tileB / 2 + twtab) / (size_t)(g.BC / bcF) > 100 * 1024) bcF /= 2;
+    if (c->ch_fbc > 0 && c->ch_fbc <= g.BC && g.BC % c->ch_fbc == 0) bcF = c->ch_fbc; /* NSB_CHAIN_FBC */
+    const size_t tileF = (tileB / 2 + twtab) / (size_t)(g.BC / bcF);
+    NsbGeom gF = g;
+    gF.BC = bcF;
     const size_t smemG = NSB_CH_TW_BYTES + (size_t)W * (want_umax ? NSB_CHG_WARP_BYTES(1) : NSB_CHG_WARP_BYTES(0));
     if (c->chain_mode == 1) {
         /* Z in bufB, P in bufA (T is dead once B has run), T' into the owners' exchange buffers */
@@ -1006,21 +1016,31 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
             if (split && pc > 0) CK(cudaStreamWaitEvent(st, c->ch_ev[1 + ((pc - 1) & 1)], 0));
             if (use_tma) {
                 prof_pre(c, PK_BETA_INV);
-                if (two_ctas) {
-                    auto k = k_chain_B_tma<128, 2>;
+                if (big) { /* 32-point factors: own instantiation, so the kernels below keep their registers */
+                    auto k = k_chain_B_tma<256, 1, true>;
+                    if (ensure_smem(c, k, smemB, true)) return -1;
+                    NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), smemB, st, gB, aB, *tm);
+                } else if (two_ctas) {
+                    auto k = k_chain_B_tma<128, 2, false>;
                     if (ensure_smem(c, k, smemB, true)) return -1;
                     NSB_LAUNCH(k, dim3(2 * c->sm_count), dim3(128), smemB, st, gB, aB, *tm);
                 } else {
-                    auto k = k_chain_B_tma<256, 1>;
+                    auto k = k_chain_B_tma<256, 1, false>;
                     if (ensure_smem(c, k, smemB, true)) return -1;
                     NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), smemB, st, gB, aB, *tm);
                 }
                 prof_post(c);
             } else {
-                auto k = k_chain_B;
-                if (ensure_smem(c, k, tileB, true)) return -1;
                 prof_pre(c, PK_BETA_INV);
-                NSB_LAUNCH(k, dim3(a.nbatch, 2, a.nslab), dim3(256), tileB, st, g, a);
+                if (big) {
+                    auto k = k_chain_B<true>;
+                    if (ensure_smem(c, k, tileB, true)) return -1;
+                    NSB_LAUNCH(k, dim3(a.nbatch, 2, a.nslab), dim3(256), tileB, st, g, a);
+                } else {
+                    auto k = k_chain_B<false>;
+                    if (ensure_smem(c, k, tileB, true)) return -1;
+                    NSB_LAUNCH(k, dim3(a.nbatch, 2, a.nslab), dim3(256), tileB, st, g, a);
+                }
                 prof_post(c);
             }
             CKL();
@@ -1051,10 +1071,18 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
             CKL();
             c->launches++;
             {
-                auto k = k_chain_F;
-                if (ensure_smem(c, k, tileF, true)) return -1;
                 prof_pre(c, PK_BETA_FWD);
-                NSB_LAUNCH(k, dim3(a.nbatch, a.nslab), dim3(256), tileF, st, g, a);
+                ChainArgs aF = a;
+                aF.nbatch = (g.X2h + 1 + bcF - 1) / bcF;
+                if (big) {
+                    auto k = k_chain_F<true>;
+                    if (ensure_smem(c, k, tileF, true)) return -1;
+                    NSB_LAUNCH(k, dim3(aF.nbatch, a.nslab), dim3(256), tileF, st, gF, aF);
+                } else {
+                    auto k = k_chain_F<false>;
+                    if (ensure_smem(c, k, tileF, true)) return -1;
+                    NSB_LAUNCH(k, dim3(aF.nbatch, a.nslab), dim3(256), tileF, st, gF, aF);
+                }
                 prof_post(c);
                 CKL();
                 c->launches++;
@@ -1678,7 +1706,7 @@ extern "C" int nsb_mgpu_setup(nsb_ctx *c, int rank, int world) {
     const NsbGeom &g = c->g;
     if (world > 1) {
         if (!(c->fast && g.Y1 == 1024 && c->chain_mode == 1))
-            return fail("slab decomposition needs Y1 == X2 == 1024 with a beta split (grids 2048..16384) and NSB_CHAIN=1");
+            return fail("slab decomposition needs Y1 == X2 == 1024 with a beta split (grids 2048..32768) and NSB_CHAIN=1");
         if ((g.ny / world) % c->ch_rows != 0) return fail("ny / world must be a multiple of %d", c->ch_rows);
     }
     if (sync_ref(c)) return -1;
