@@ -416,7 +416,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=16384, help="grid size (nx = ny)")
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=16384,
+                    help="grid size (nx = ny); under torchrun use --grid (its parser takes --n for its own options)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-n", type=int, default=2048, help="grid of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=3, help="timed CPU steps (0 = skip cpu_baseline)")
