@@ -88,8 +88,7 @@ def test_emu_chain(nsb, emu_lib, oracles, monkeypatch, mode, nx, ny, plan):
 
 
 @pytest.mark.parametrize("nx,ny,plan", [
-    (1024, 64, dict(x2=1024, y1=2)),           # X1 = 1, Y2 = 32: 32-row slabs, one y1 value each, 2 slabs
-    (2048, 64, dict(x2=1024, y1=2)),           # X1 = 2, Y2 = 32
+    (2048, 64, dict(x2=1024, y1=2)),           # X1 = 2, Y2 = 32: 32-row slabs, one y1 value each, 2 slabs
     (32768, 16, dict(x2=1024, y1=4)),          # X1 = 32, Y2 = 4: 22 column segments, 4-column B batches
 ])
 def test_emu_chain_32_point_factors(nsb, emu_lib, oracles, monkeypatch, nx, ny, plan):
@@ -97,7 +96,7 @@ def test_emu_chain_32_point_factors(nsb, emu_lib, oracles, monkeypatch, nx, ny, 
     plus the generic c2r / r2c kernels at the same factorisation (k_beta_*<32, .> / <., 32>).
     F runs with the 8-column batches it takes at 32768^2 (automatic only when its tile exceeds 100 KB)."""
     monkeypatch.setenv("NSB_CHAIN_FBC", "8")
-    pc.check_per_step(nsb, emu_lib, oracles, best_oracle_kind(oracles), nx, ny, 2, hv=HV,
+    pc.check_per_step(nsb, emu_lib, oracles, best_oracle_kind(oracles), nx, ny, 1 if nx > 4096 else 2, hv=HV,
                       forcing=dict(kind="white"), **plan)
     pc.check_transforms(nsb, emu_lib, oracles, best_oracle_kind(oracles), nx, ny, **plan)
 
