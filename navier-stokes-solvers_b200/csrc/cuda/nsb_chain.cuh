@@ -507,7 +507,12 @@ __device__ __forceinline__ void chain_B_step2p(const NsbGeom &g, const ChainArgs
     const int nseg = a.nd + a.nm;
     const bool special_batch = (kb == 0) || (kb <= g.X2h && kb + g.BC > g.X2h);
     for (int w = threadIdx.x; w < 2 * a.R * g.BC; w += blockDim.x) {
-        const int half = w & 1, item = w >> 1;
+        /* the +- halves of an item sit in neighbouring lanes only where they must exchange (the two
+         * batches with a self-conjugate bin); elsewhere each half takes a contiguous run of items, so the
+         * 8 lanes of a 128-bit shared-memory phase read 8 distinct values instead of 4 pairs */
+        const int nitem = a.R * g.BC;
+        const int half = special_batch ? (w & 1) : (w >= nitem ? 1 : 0);
+        const int item = special_batch ? (w >> 1) : (w - half * nitem);
         const int r = item / g.BC, cc = item - r * g.BC;
         const int k2 = kb + cc;
         const bool valid = k2 <= g.X2h;

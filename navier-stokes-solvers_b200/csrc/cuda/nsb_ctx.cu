@@ -77,6 +77,7 @@ struct nsb_ctx {
     int chain_mode;
     int ch_rows; /* y rows per chain slab (ChainArgs::R) */
     int ch_fbc;  /* F batch width override (0 = automatic) */
+    int ch_fthreads;
     cd *chZ, *chP;     /* L2-resident rings of the persistent kernel */
     unsigned *chCtr;   /* ticket + per-slab completion counters */
     int ch_slotZ, ch_slotP, ch_leadG, ch_leadF, ch_ctas, ch_btma;
@@ -273,6 +274,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->ch_btma = env_int("NSB_CHAIN_BTMA", 1);
     c->ch_bbc = env_int("NSB_CHAIN_BBC", -1);
     c->ch_fbc = env_int("NSB_CHAIN_FBC", 0);
+    c->ch_fthreads = env_int("NSB_CHAIN_FTHREADS", 128) == 256 ? 256 : 128; /* F with 32-point factors only */
     c->ch_pieces = env_int("NSB_CHAIN_PIECES", 0);         /* 0 = automatic */
     c->ch_gpersist = env_int("NSB_CHAIN_GPERSIST", 0); /* measured: the persistent G is 6 % slower (2.93 vs 2.77 ms) */
     c->alpha_cols = env_int("NSB_ALPHA_COLS", 4) == 8 ? 8 : 4;
@@ -1075,9 +1077,11 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
                 ChainArgs aF = a;
                 aF.nbatch = (g.X2h + 1 + bcF - 1) / bcF;
                 if (big) {
+                    /* 182 registers (one 32-point array per thread): 128-thread CTAs so that two of them,
+                     * with their 90 KB tiles, share an SM and overlap each other's load and barrier phases */
                     auto k = k_chain_F<true>;
                     if (ensure_smem(c, k, tileF, true)) return -1;
-                    NSB_LAUNCH(k, dim3(aF.nbatch, a.nslab), dim3(256), tileF, st, gF, aF);
+                    NSB_LAUNCH(k, dim3(aF.nbatch, a.nslab), dim3(c->ch_fthreads), tileF, st, gF, aF);
                 } else {
                     auto k = k_chain_F<false>;
                     if (ensure_smem(c, k, tileF, true)) return -1;
