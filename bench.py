@@ -351,7 +351,10 @@ def run_gpu_arm(args):
                          "achieved": 512.0 * (float(n) * n / (ms_step * 1e-3)) / 1e9 / world,
                          "frac": 512.0 * (float(n) * n / (ms_step * 1e-3)) / 1e9 / world / peak,
                          "note": "per GPU: 512 B x grid-point-steps/s / n_gpus against one GPU's HBM peak"},
-                "per_kernel": per_kernel}
+                "per_kernel": per_kernel,
+                "per_kernel_note": "CUDA events around every launch need one stream: measured in a separate pass "
+                                   "with the chain in ONE slab range; in the timed region B, G, F run as up to 16 "
+                                   "slab ranges on two streams (profiles/README.md has the ncu launch list)"}
     if world > 1:
         # NVLink: every stage pushes 4 T fields + 1 T' field of the retained columns; (world-1)/world of
         # a rank's share leaves the GPU. SURVEY 8e contract figure (unpruned) alongside the real bytes.
