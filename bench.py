@@ -367,6 +367,11 @@ def run_gpu_arm(args):
                               "peak_GBs": 770.0, "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
                               "frac": contract / (ms_step * 1e-3) / 1e9 / 770.0}
 
+    # fingerprint of the whole run: t and dt after all steps depend on max|u| over the whole field at every
+    # step, so runs with the same --warmup/--steps must agree bit for bit across GPU counts
+    fingerprint = {"t": float(s.s.t).hex(), "dt": float(s.s.dt).hex(), "t_dec": s.s.t, "dt_dec": s.s.dt,
+                   "steps_taken": args.warmup + args.steps + e2e_steps + prof_steps}
+
     # ---- strict drop-in loop (EAGER): bounded, single GPU only, small step count
     e2e_eager = None
     if world == 1 and args.eager_steps > 0:
@@ -381,10 +386,6 @@ def run_gpu_arm(args):
                      "h2d_bytes_per_step": m_bytes + 2 * n_bytes, "d2h_bytes_per_step": 4 * m_bytes + 3 * n_bytes,
                      "api": "ns_spectral_compute_cfl_timestep + ns_spectral_advance_rk4, NS_SYNC_EAGER (pageable host arrays)"}
 
-    # fingerprint of the whole run: t and dt after all steps depend on max|u| over the whole field at every
-    # step, so runs with the same --warmup/--steps must agree bit for bit across GPU counts
-    fingerprint = {"t": float(s.s.t).hex(), "dt": float(s.s.dt).hex(), "t_dec": s.s.t, "dt_dec": s.s.dt,
-                   "steps_taken": args.warmup + args.steps + e2e_steps + prof_steps}
     host.ns_forcing_state_free(C.byref(fs))
     plan = (C.c_int * 8)()
     nsblib.nsb_get_plan(ctx, plan)
