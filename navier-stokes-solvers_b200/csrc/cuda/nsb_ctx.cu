@@ -963,9 +963,11 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
          * slabs) every split is slower. True co-residency (one B CTA + one G CTA per SM, also with a
          * 16-column one-stage B) was slower still, 54-58 ms: B needs all eight warps of an SM; the gain
          * comes from overlapping the kernels' tails. */
-        /* slab-decomposed over 8 devices (128 slabs each at 16384^2), measured: 1 / 2 / 4 / 8 / 16 ranges
-         * 8.93 / 8.83 / 8.70 / 9.01 / 9.23 ms per step */
-        const int auto_pieces = total_slabs >= 512 ? 16 : ((c->mg_world > 1 && !big && total_slabs == 128) ? 4 : 1);
+        /* slab-decomposed, ranges of 32 slabs, measured at 16384^2: 8 devices (128 slabs each) 1 / 2 / 4 / 8 /
+         * 16 ranges 8.93 / 8.83 / 8.70 / 9.01 / 9.23 ms per step; 4 devices (256 slabs each) 1 / 4 / 8 ranges
+         * 15.55 / 15.48 / 15.18 ms */
+        const int auto_pieces =
+            total_slabs >= 512 ? 16 : ((c->mg_world > 1 && !big && total_slabs >= 128) ? total_slabs / 32 : 1);
         int pieces = c->prof_on ? 1 : (c->ch_pieces > 0 ? c->ch_pieces : auto_pieces);
         if (pieces > total_slabs) pieces = total_slabs;
         const bool split = pieces > 1;
