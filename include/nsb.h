@@ -140,6 +140,15 @@ int nsb_spectral_stats(nsb_ctx *c, double out[6]);
  * shell b = (int)(sqrt(k2) + 0.5), b < nbins (host arrays of nbins entries). Synchronous. */
 int nsb_energy_spectrum(nsb_ctx *c, int nbins, double *ek_sum, int *count);
 
+/* Re and cfl_factor are read live from NSSpectralData by the reference (spectral_time_integration.c:
+ * 22-24, 52); the host layer pushes the caller's current values before every step / CFL evaluation. */
+int nsb_set_physics(nsb_ctx *c, double Re, double cfl_factor);
+
+/* max |f| over a physical field, and f *= s, on the device (the two host loops of the build-defined
+ * random-phase initial condition, SURVEY 8d, without moving the field to the host). */
+int nsb_phys_absmax(nsb_ctx *c, int field_phys, double *out);
+int nsb_phys_scale(nsb_ctx *c, int field_phys, double s);
+
 /* device-side scalars: last dt, time, number of steps taken. Synchronous. */
 int nsb_get_state(nsb_ctx *c, double *dt, double *t, int *steps);
 int nsb_set_time(nsb_ctx *c, double t);
@@ -187,6 +196,13 @@ int nsb_mgpu_group_step(nsb_ctx **ctxs, int n, double dt);
  * devices (gather) or publish it to all devices after the host changed it (scatter) */
 int nsb_mgpu_group_gather(nsb_ctx **ctxs, int n);
 int nsb_mgpu_group_scatter(nsb_ctx **ctxs, int n);
+
+/* Order-independent, exactly combinable fingerprint of the RK state omega_hat over the retained
+ * columns this device owns ([col0, col1), all ky rows): out[0] = XOR, out[1] = wrapping 64-bit sum of
+ * the IEEE-754 bit patterns of every real and imaginary part. XOR / add the results of all ranks of a
+ * slab-decomposed run and compare with the one-device run: equal <=> the fields agree bit for bit
+ * (up to XOR/sum collisions). Synchronous. */
+int nsb_state_checksum(nsb_ctx *c, unsigned long long out[2]);
 
 /* number of kernels this library has launched on this context */
 long long nsb_launch_count(nsb_ctx *c);

@@ -99,6 +99,7 @@ def load_nsb(path=None):
         "nsb_spectral_stats": [C.c_void_p, c_double_p],
         "nsb_energy_spectrum": [C.c_void_p, C.c_int, c_double_p, C.POINTER(C.c_int)],
         "nsb_mgpu_group_gather": [C.POINTER(C.c_void_p), C.c_int],
+        "nsb_state_checksum": [C.c_void_p, C.POINTER(C.c_ulonglong)],
         "nsb_mgpu_group_scatter": [C.POINTER(C.c_void_p), C.c_int],
     }
     for name, args in sigs.items():
@@ -244,6 +245,12 @@ class NsbContext:
         ek, cnt = (C.c_double * nbins)(), (C.c_int * nbins)()
         self._ck(self.lib.nsb_energy_spectrum(self.h, nbins, ek, cnt))
         return np.array(ek[:]), np.array(cnt[:])
+
+    def state_checksum(self):
+        """(xor, wrapping sum) of the bit patterns of omega_hat over the own retained columns"""
+        out = (C.c_ulonglong * 2)()
+        self._ck(self.lib.nsb_state_checksum(self.h, out))
+        return int(out[0]), int(out[1])
 
     def state(self):
         dt, t, st = C.c_double(), C.c_double(), C.c_int()

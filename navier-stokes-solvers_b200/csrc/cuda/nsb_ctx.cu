@@ -612,6 +612,14 @@ extern "C" int nsb_set_hyperviscosity(nsb_ctx *c, const nsb_hyperviscosity *h) {
     return 0;
 }
 
+extern "C" int nsb_set_physics(nsb_ctx *c, double Re, double cfl_factor) {
+    if (!c) return fail("null context");
+    if (!(Re > 0.0) || !(cfl_factor > 0.0)) return fail("nsb_set_physics: Re and cfl_factor must be positive");
+    c->prm.Re = Re;
+    c->prm.cfl_factor = cfl_factor;
+    return 0;
+}
+
 extern "C" int nsb_set_forcing(nsb_ctx *c, int ib, int jb, const double *box) {
     if (!c) return fail("null context");
     CK(cudaSetDevice(c->device));
@@ -1345,9 +1353,9 @@ extern "C" int nsb_hyperviscosity_post_step(nsb_ctx *c, int state_hat, double dt
     return 0;
 }
 
-static int launch_cfl(nsb_ctx *c) {
+static int launch_cfl(nsb_ctx *c, bool local = false) {
     const double dx_min = fmin(c->prm.Lx / c->g.nx, c->prm.Ly / c->g.ny);
-    if (c->mg_world > 1) {
+    if (c->mg_world > 1 && !local) {
         /* max |u|^2 over the slabs of all devices, read from their scalar blocks (peer memory) */
         NsbPeerScalars ps;
         for (int p = 0; p < NSB_MAXP; ++p) ps.sc[p] = c->mg_sc[p < c->mg_world ? p : 0];
@@ -1383,7 +1391,7 @@ extern "C" int nsb_cfl_timestep_uv(nsb_ctx *c, double *dt_out) {
                (const double *)v, c->N, &c->d_sc->umax_bits);
     CKL();
     c->launches++;
-    if (launch_cfl(c) || fetch_scalars(c)) return -1;
+    if (launch_cfl(c, true) || fetch_scalars(c)) return -1; /* whole field on this device: no peer maxima */
     *dt_out = c->h_sc->dt;
     return 0;
 }
@@ -1398,7 +1406,7 @@ extern "C" int nsb_cfl_timestep(nsb_ctx *c, double *dt_out) {
     const cd *src[4] = {(const cd *)w, nullptr, nullptr, nullptr};
     double *dst[4] = {nullptr, nullptr, nullptr, nullptr};
     if (inverse_fields(c, NSB_SRC_VEL, 2, src, dst, true, false)) return -1;
-    if (launch_cfl(c) || fetch_scalars(c)) return -1;
+    if (launch_cfl(c, true) || fetch_scalars(c)) return -1;
     *dt_out = c->h_sc->dt;
     return 0;
 }
@@ -1667,6 +1675,54 @@ extern "C" int nsb_diagnostics_phys(nsb_ctx *c, double out[4]) {
     return 0;
 }
 
+__global__ void __launch_bounds__(256) k_phys_absmax(const double *f, size_t n, unsigned long long *bits) {
+    NSB_DYN_SMEM(double, red);
+    double m = 0.0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        m = fmax(m, fabs(f[k]));
+    nsb_block_max_to_global(m, bits, red);
+}
+
+__global__ void __launch_bounds__(256) k_phys_scale(double *f, size_t n, double s) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        f[k] = __dmul_rn(f[k], s);
+}
+
+extern "C" int nsb_phys_absmax(nsb_ctx *c, int field, double *out) {
+    if (!c || !out) return fail("nsb_phys_absmax: null argument");
+    if (!field_is_phys(field)) return fail("nsb_phys_absmax: not a physical field");
+    CK(cudaSetDevice(c->device));
+    void *f;
+    if (get_field(c, field, &f)) return -1;
+    CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
+    size_t blocks = (c->N + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    auto k = k_phys_absmax;
+    NSB_LAUNCH(k, dim3((unsigned)blocks), dim3(256), 256 * sizeof(double), c->stream, (const double *)f, c->N,
+               &c->d_sc->umax_bits);
+    CKL();
+    c->launches++;
+    if (fetch_scalars(c)) return -1;
+    memcpy(out, &c->h_sc->umax_bits, sizeof(double));
+    CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
+    return 0;
+}
+
+extern "C" int nsb_phys_scale(nsb_ctx *c, int field, double s) {
+    if (!c) return fail("null context");
+    if (!field_is_phys(field)) return fail("nsb_phys_scale: not a physical field");
+    CK(cudaSetDevice(c->device));
+    void *f;
+    if (get_field(c, field, &f)) return -1;
+    size_t blocks = (c->N + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    auto k = k_phys_scale;
+    NSB_LAUNCH(k, dim3((unsigned)blocks), dim3(256), 0, c->stream, (double *)f, c->N, s);
+    CKL();
+    c->launches++;
+    return 0;
+}
+
 extern "C" int nsb_get_state(nsb_ctx *c, double *dt, double *t, int *steps) {
     if (!c) return fail("null context");
     CK(cudaSetDevice(c->device));
@@ -1913,6 +1969,51 @@ extern "C" int nsb_mgpu_group_scatter(nsb_ctx **cs, int n) {
         cs[r]->k_truth = 0;
         cs[r]->masked_nonzero = cs[0]->masked_nonzero;
     }
+    return 0;
+}
+
+/* ---------------------------------------------------- state fingerprint */
+
+__global__ void __launch_bounds__(256) k_state_checksum(NsbGeom g, const cd *W, int c0, int c1, unsigned long long *out) {
+    const int w = c1 - c0;
+    const size_t total = (size_t)w * g.ny;
+    unsigned long long x = 0ull, s = 0ull;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(k / w), i = c0 + (int)(k - (size_t)j * w);
+        const cd v = W[(size_t)j * g.nkx + i];
+        const unsigned long long a = (unsigned long long)__double_as_longlong(v.x);
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v.y);
+        x ^= a ^ (b << 1 | b >> 63); /* rotate the imaginary part so that re == im does not cancel */
+        s += a + 3ull * b;
+    }
+#ifndef NSB_EMULATE
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        x ^= __shfl_xor_sync(0xffffffffu, x, off);
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+    }
+    if ((threadIdx.x & 31) != 0) return;
+#endif
+    atomicXor(out, x);
+    atomicAdd(out + 1, s);
+}
+
+extern "C" int nsb_state_checksum(nsb_ctx *c, unsigned long long out[2]) {
+    if (!c || !out) return fail("nsb_state_checksum: null argument");
+    CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
+    void *w;
+    if (get_field(c, NSB_OMEGA_HAT, &w)) return -1;
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(c->d_sc->stats);
+    CK(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), c->stream));
+    if (c->mg_c1 > c->mg_c0) {
+        auto k = k_state_checksum;
+        NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 0, c->stream, c->g, (const cd *)w, c->mg_c0, c->mg_c1, d);
+        CKL();
+        c->launches++;
+    }
+    CK(cudaMemcpyAsync(out, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -855,9 +855,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gamma1024(NsbGeom g, GammaFas
             nsb_mbar_wait(bar, phase);
             phase ^= 1u;
             nsb_load_hermitian1024(x, L, L + 513, a.nvalid_in, lane);
-#ifdef NSB_DEBUG_G
-            if (lane == 1 && pair == 0) { const cd *A0 = a.in + (size_t)(2*pair+comb)*g.PH; printf("comb %d L[1]=(%g,%g) A[1]=(%g,%g) B: L=(%g,%g) g=(%g,%g) x0=(%g,%g)\n", comb, L[1].x, L[1].y, A0[1].x, A0[1].y, L[514].x, L[514].y, (A0+g.fsH)[1].x, (A0+g.fsH)[1].y, x[0].x, x[0].y); }
-#endif
             __syncwarp();
             issue(pair, comb, 1);
             nsb_fft1024_warp<true>(x, T, TW, lane);

@@ -205,6 +205,12 @@ int main(int argc, char *argv[]) {
         /* batches of 10 steps between console lines; single steps near t_end so the loop
          * stops on the same step as the reference's per-step test */
         int chunk = 10 - step % 10;
+        /* never step past the next multiple of an interval the loop acts on (the reference tests
+         * `step % interval == 0` after every single step: main_spectral.c:51-64) */
+        if (output_interval > 0 && output_interval - step % output_interval < chunk)
+            chunk = output_interval - step % output_interval;
+        if (restart_save[0] && restart_interval > 0 && restart_interval - step % restart_interval < chunk)
+            chunk = restart_interval - step % restart_interval;
         if (data->dt > 0.0 && (t_final - data->t) < 2.0 * chunk * data->dt) chunk = 1;
         if (step == 0) chunk = 1;
         if (max_steps > 0 && step + chunk > max_steps) chunk = max_steps - step;

@@ -181,6 +181,15 @@ static void push_hyperviscosity(NSSpectralData *d) {
     for (int r = 1; r < b->ngpus; ++r) NSB_OK(nsb_set_hyperviscosity(b->group[r], &p), "hyperviscosity");
 }
 
+/* the reference reads data->Re and data->cfl_factor at every use (spectral_time_integration.c:22-24,
+ * 52): hand the caller's current values to every device context before a step / CFL evaluation */
+static void push_physics(NSSpectralData *d, const char *where) {
+    Backend *b = backend_of(d);
+    if (!b || !b->ctx) return;
+    NSB_OK(nsb_set_physics(b->ctx, d->Re, d->cfl_factor), where);
+    for (int r = 1; r < b->ngpus; ++r) NSB_OK(nsb_set_physics(b->group[r], d->Re, d->cfl_factor), where);
+}
+
 /* spectral_initialization.c:57-69: "plan creation" = device context creation */
 void ns_spectral_initialize_fft_plans(NSSpectralData *d) {
     Backend *b = backend_of(d);
@@ -255,7 +264,12 @@ static unsigned long long sm64(unsigned long long *st) {
     return z ^ (z >> 31);
 }
 
-/* SURVEY 8d (build-defined; the reference has no turbulence initial condition) */
+/* SURVEY 8d (build-defined; the reference has no turbulence initial condition): for idx = j*nkx + i
+ * ascending over ALL modes one splitmix64 draw -> phase, omega_hat = a(k) e^{i theta}, a = k^2 exp(-(k/k0)^2);
+ * c2r; scale to max|omega| = max_omega; r2c (normalise + mask + Hermitian projection); derivatives.
+ * Same definition as nsref_random_phase_init of the oracle build. Where exp() underflows (a == 0
+ * exactly) the trigonometry is skipped but the draw is still consumed. Under NS_SYNC_LAZY the peak
+ * search and the rescaling run on the device and no field is copied back (16384^2: 2 GB up, 0 down). */
 int ns_spectral_initialize_random_phase(NSSpectralData *d, unsigned long long seed, double k0, double max_omega) {
     static const char *W = "ns_spectral_initialize_random_phase";
     nsb_ctx *c = ctx_of(d, W);
@@ -265,24 +279,31 @@ int ns_spectral_initialize_random_phase(NSSpectralData *d, unsigned long long se
         const int band = (j <= ny / 2) ? j : j - ny;
         for (int i = 0; i < nkx; ++i) {
             const double un = (double)(sm64(&st) >> 11) * (1.0 / 9007199254740992.0);
-            const double theta = 2.0 * M_PI * un;
             const double kk = sqrt((double)i * i + (double)band * band);
-            const double a = kk * kk * exp(-(kk / k0) * (kk / k0));
-            d->omega_hat[(size_t)j * nkx + i] = a * cos(theta) + I * (a * sin(theta));
+            const double e = (kk / k0) * (kk / k0);
+            const size_t idx = (size_t)j * nkx + i;
+            if (e > 745.2) { /* exp(-e) == 0 in binary64 */
+                if (creal(d->omega_hat[idx]) != 0.0 || cimag(d->omega_hat[idx]) != 0.0) d->omega_hat[idx] = 0.0;
+                continue;
+            }
+            const double theta = 2.0 * M_PI * un;
+            const double a = kk * kk * exp(-e);
+            d->omega_hat[idx] = a * cos(theta) + I * (a * sin(theta));
         }
     }
     d->omega_hat[0] = 0.0;
     upload(d, NSB_OMEGA_HAT, d->omega_hat, W);
     const int src = NSB_OMEGA_HAT, dst = NSB_OMEGA;
     NSB_OK(nsb_spectral_to_physical(c, 1, &src, &dst), W);
-    download(d, NSB_OMEGA, d->omega, W);
     double peak = 0.0;
-    const size_t n = n_phys(d);
-    for (size_t k = 0; k < n; ++k) peak = fmax(peak, fabs(d->omega[k]));
+    NSB_OK(nsb_phys_absmax(c, NSB_OMEGA, &peak), W);
     const double scale = (peak > 0.0) ? max_omega / peak : 0.0;
-    for (size_t k = 0; k < n; ++k) d->omega[k] *= scale;
-    upload(d, NSB_OMEGA, d->omega, W);
+    NSB_OK(nsb_phys_scale(c, NSB_OMEGA, scale), W);
     NSB_OK(nsb_physical_to_spectral(c, NSB_OMEGA, NSB_OMEGA_HAT), W);
+    if (lazy(d)) {
+        NSB_OK(nsb_compute_derivatives(c), W);
+        return 0;
+    }
     download(d, NSB_OMEGA_HAT, d->omega_hat, W);
     refresh_derived_to_host(d, W);
     return 0;
@@ -372,6 +393,7 @@ void ns_spectral_compute_nonlinear_terms(NSSpectralData *d) {
 double ns_spectral_compute_cfl_timestep(NSSpectralData *d) {
     static const char *W = "ns_spectral_compute_cfl_timestep";
     nsb_ctx *c = ctx_of(d, W);
+    push_physics(d, W);
     double dt = 0.0;
     if (lazy(d)) {
         NSB_OK(nsb_cfl_timestep(c, &dt), W);
@@ -392,11 +414,17 @@ static int push_sfd_if_needed(NSSpectralData *d, const char *where) {
     return 0;
 }
 
-/* dense forcing array -> bounding box of its non-zero entries -> device */
+/* the same forcing box on every device of a group (each applies it to its own columns) */
+static void set_forcing_all(NSSpectralData *d, int ib, int jb, const double *box, const char *where) {
+    Backend *b = backend_of(d);
+    NSB_OK(nsb_set_forcing(b->ctx, ib, jb, box), where);
+    for (int r = 1; r < b->ngpus; ++r) NSB_OK(nsb_set_forcing(b->group[r], ib, jb, box), where);
+}
+
+/* dense forcing array -> bounding box of its non-zero entries -> device(s) */
 static void push_dense_forcing(NSSpectralData *d, const fftw_complex *f, const char *where) {
-    nsb_ctx *c = ctx_of(d, where);
     if (!f) {
-        NSB_OK(nsb_set_forcing(c, 0, 0, NULL), where);
+        set_forcing_all(d, 0, 0, NULL, where);
         return;
     }
     int ib = 0, jb = 0;
@@ -418,14 +446,35 @@ static void push_dense_forcing(NSSpectralData *d, const fftw_complex *f, const c
         const int j = (band >= 0) ? band : band + d->ny;
         for (int i = 0; i <= ib; ++i) box[(size_t)(band + jb) * (ib + 1) + i] = f[(size_t)j * d->nkx + i];
     }
-    NSB_OK(nsb_set_forcing(c, ib, jb, (const double *)box), where);
+    set_forcing_all(d, ib, jb, (const double *)box, where);
     free(box);
+}
+
+/* one RK4 step with step size dt (dt <= 0: CFL step computed on the device) on the single device or,
+ * after ns_spectral_backend_init(n > 1), slab-decomposed on the device group: what the single-device
+ * entry points did to omega_hat on the first device since the last group step is published first */
+static void step_devices(NSSpectralData *d, double dt, const char *where) {
+    Backend *b = backend_of(d);
+    if (b->ngpus > 1) {
+        if (b->dirty) NSB_OK(nsb_mgpu_group_scatter(b->group, b->ngpus), where);
+        b->dirty = 0;
+        NSB_OK(nsb_mgpu_group_step(b->group, b->ngpus, dt), where);
+        b->gathered = 0;
+    } else {
+        NSB_OK(nsb_rk4_step(b->ctx, dt), where);
+    }
+}
+
+static void set_time_all(NSSpectralData *d, const char *where) {
+    Backend *b = backend_of(d);
+    NSB_OK(nsb_set_time(b->ctx, d->t), where);
+    for (int r = 1; r < b->ngpus; ++r) NSB_OK(nsb_set_time(b->group[r], d->t), where);
 }
 
 /* spectral_time_integration.c:34-106 (+ f_hat) */
 int ns_spectral_advance_rk4_forced(NSSpectralData *d, const fftw_complex *forcing) {
     static const char *W = "ns_spectral_advance_rk4";
-    nsb_ctx *c = ctx_of(d, W);
+    ctx_of(d, W);
     if (!(d->dt > 0.0)) {
         set_error("advance_rk4: data->dt must be positive (got %g)", d->dt);
         return -1;
@@ -435,15 +484,16 @@ int ns_spectral_advance_rk4_forced(NSSpectralData *d, const fftw_complex *forcin
         upload(d, NSB_OMEGA_HAT, d->omega_hat, W);
         sfd = push_sfd_if_needed(d, W);
     }
+    push_physics(d, W);
     push_dense_forcing(d, forcing, W);
-    NSB_OK(nsb_rk4_step(c, d->dt), W);
+    step_devices(d, d->dt, W);
     d->t += d->dt;
     if (!lazy(d)) {
         download(d, NSB_OMEGA_HAT, d->omega_hat, W);
         if (sfd) download(d, NSB_SFD_HAT, d->sfd_hat, W);
         refresh_derived_to_host(d, W);
     }
-    NSB_OK(nsb_set_time(c, d->t), W);
+    set_time_all(d, W);
     return 0;
 }
 
@@ -488,40 +538,29 @@ int ns_spectral_run_steps(NSSpectralData *d, int n, NSForcingState *fs) {
         upload(d, NSB_OMEGA_HAT, d->omega_hat, W);
         sfd = push_sfd_if_needed(d, W);
     }
-    NSB_OK(nsb_set_time(c, d->t), W);
+    push_physics(d, W);
+    set_time_all(d, W);
     if (fs && bind_forcing(d, fs) != 0) return -1;
     const int group = b->ngpus > 1;
-    if (group) {
-        if (fs && fs->config.type == NS_FORCING_COLORED_NOISE) {
-            set_error("%s: coloured forcing needs the CFL step on the host before every step; not supported on a "
-                      "device group", W);
-            return -1;
-        }
-        /* publish what the single-device entry points did to omega_hat since the last group step */
-        if (b->dirty) NSB_OK(nsb_mgpu_group_scatter(b->group, b->ngpus), W);
-        b->dirty = 0;
-        for (int r = 1; r < b->ngpus; ++r) NSB_OK(nsb_set_time(b->group[r], d->t), W);
-    }
-    for (int r = 0; r < (group ? b->ngpus : 1); ++r)
-        if (!fs) NSB_OK(nsb_set_forcing(group ? b->group[r] : c, 0, 0, NULL), W);
+    if (!fs) set_forcing_all(d, 0, 0, NULL, W);
     for (int s = 0; s < n; ++s) {
         double dt = 0.0; /* 0 = CFL step computed on the device inside the step */
         if (fs) {
-            /* coloured noise needs dt before the stream is consumed (forcing.c:138-147) */
-            if (fs->config.type == NS_FORCING_COLORED_NOISE) NSB_OK(nsb_cfl_timestep(c, &dt), W);
+            /* coloured noise needs dt before the stream is consumed (forcing.c:138-147): the CFL step is
+             * evaluated first (on a group: from the state gathered into the first device, 8 bytes back) and
+             * handed to the step, exactly the reference's `data->dt = cfl(); advance_rk4()` order */
+            if (fs->config.type == NS_FORCING_COLORED_NOISE) {
+                c = ctx_ro(d, W);
+                NSB_OK(nsb_cfl_timestep(c, &dt), W);
+            }
             ns_forcing_generate_box(fs, dt, b->forcing_idx, b->ib, b->jb, b->forcing_box);
-            for (int r = 0; r < (group ? b->ngpus : 1); ++r)
-                NSB_OK(nsb_set_forcing(group ? b->group[r] : c, b->ib, b->jb, (const double *)b->forcing_box), W);
+            set_forcing_all(d, b->ib, b->jb, (const double *)b->forcing_box, W);
         }
-        if (group) {
-            NSB_OK(nsb_mgpu_group_step(b->group, b->ngpus, dt), W);
-            b->gathered = 0;
-        } else {
-            NSB_OK(nsb_rk4_step(c, dt), W);
-        }
+        step_devices(d, dt, W);
     }
+    (void)group;
     int steps = 0;
-    NSB_OK(nsb_get_state(c, &d->dt, &d->t, &steps), W);
+    NSB_OK(nsb_get_state(b->ctx, &d->dt, &d->t, &steps), W);
     if (!lazy(d)) {
         download(d, NSB_OMEGA_HAT, d->omega_hat, W);
         if (sfd) download(d, NSB_SFD_HAT, d->sfd_hat, W);
@@ -725,7 +764,10 @@ void ns_spectral_hyperviscosity_set(NSSpectralData *d, const NSSpectralHypervisc
     if (h->sfd_enabled) {
         Backend *b = backend_of(d);
         if (b && b->ctx && lazy(d)) {
-            NSB_OK(nsb_copy(b->ctx, NSB_SFD_HAT, NSB_OMEGA_HAT), "ns_spectral_hyperviscosity_set");
+            /* through ctx_of: on a device group the columns of all devices are gathered first and the
+             * seeded filter state is published again before the next group step */
+            NSB_OK(nsb_copy(ctx_of(d, "ns_spectral_hyperviscosity_set"), NSB_SFD_HAT, NSB_OMEGA_HAT),
+                   "ns_spectral_hyperviscosity_set");
         } else {
             memcpy(d->sfd_hat, d->omega_hat, m * sizeof(fftw_complex));
             if (b && b->ctx) upload(d, NSB_SFD_HAT, d->sfd_hat, "ns_spectral_hyperviscosity_set");
@@ -916,9 +958,15 @@ int ns_spectral_load_state(NSSpectralData *d, NSForcingState *fs, const char *fi
                   hd.Ly, d->nx, d->ny, d->Lx, d->Ly);
         return -1;
     }
+    if (hd.Re != d->Re) {
+        fclose(fp);
+        set_error("%s: file was written at Re = %.17g, the solver runs at Re = %.17g", W, hd.Re, d->Re);
+        return -1;
+    }
     if (fs && hd.has_forcing &&
         (fs->nkx != d->nkx || fs->nky != d->nky || fs->active_modes != hd.active_modes ||
-         fs->config.type != hd.fcfg.type || (hd.has_colored && !fs->colored_state))) {
+         fs->config.type != hd.fcfg.type || fs->config.kmin != hd.fcfg.kmin || fs->config.kmax != hd.fcfg.kmax ||
+         (hd.has_colored && !fs->colored_state))) {
         fclose(fp);
         set_error("%s: forcing state was initialised with a different band or type than the file's", W);
         return -1;
@@ -939,6 +987,7 @@ int ns_spectral_load_state(NSSpectralData *d, NSForcingState *fs, const char *fi
     upload(d, NSB_OMEGA_HAT, d->omega_hat, W);
     if (hd.has_sfd) upload(d, NSB_SFD_HAT, d->sfd_hat, W);
     NSB_OK(nsb_set_time(c, d->t), W);
+    push_physics(d, W); /* the file's cfl_factor is live on the device(s) from here on */
     if (fs && hd.has_forcing) {
         fs->config = hd.fcfg;
         fs->rng_state = hd.rng_state;

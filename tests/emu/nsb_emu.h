@@ -93,6 +93,8 @@ static inline unsigned long long atomicMax(unsigned long long *a, unsigned long 
 static inline double atomicAdd(double *a, double v) { double o = *a; *a = o + v; return o; }
 static inline int atomicAdd(int *a, int v) { int o = *a; *a = o + v; return o; }
 static inline unsigned atomicAdd(unsigned *a, unsigned v) { unsigned o = *a; *a = o + v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long *a, unsigned long long v) { unsigned long long o = *a; *a = o + v; return o; }
+static inline unsigned long long atomicXor(unsigned long long *a, unsigned long long v) { unsigned long long o = *a; *a = o ^ v; return o; }
 static inline unsigned atomicOr(unsigned *a, unsigned v) { unsigned o = *a; *a = o | v; return o; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }

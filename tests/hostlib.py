@@ -6,7 +6,7 @@ import os
 
 import numpy as np
 
-import orc
+import ns_structs as orc  # struct layouts / views of the public headers only (no oracle code)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PRODUCT = os.path.join(ROOT, "navier-stokes-solvers_b200", "lib", "libns_spectral.so")
@@ -69,7 +69,7 @@ NSB_SYMBOLS = [
     "nsb_launch_count",
     "nsb_mgpu_setup", "nsb_mgpu_partition", "nsb_mgpu_export", "nsb_mgpu_import", "nsb_mgpu_link_local",
     "nsb_mgpu_group_step", "nsb_mgpu_group_gather", "nsb_mgpu_group_scatter", "nsb_spectral_stats",
-    "nsb_energy_spectrum",
+    "nsb_energy_spectrum", "nsb_state_checksum", "nsb_phys_absmax", "nsb_phys_scale", "nsb_set_physics",
 ]
 
 

@@ -18,59 +18,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 
-c_double_p = C.POINTER(C.c_double)
-c_int_p = C.POINTER(C.c_int)
-
-
-class Hyperviscosity(C.Structure):
-    _fields_ = [
-        ("enabled", C.c_int),
-        ("coefficient", C.c_double),
-        ("order", C.c_int),
-        ("cutoff_ratio", C.c_double),
-        ("sfd_strength", C.c_double),
-        ("sfd_timescale", C.c_double),
-        ("sfd_enabled", C.c_int),
-        ("kmax", C.c_double),
-        ("cutoff_wavenumber", C.c_double),
-        ("inv_bandwidth", C.c_double),
-    ]
-
-
-REAL_FIELDS = ["u", "v", "p", "omega", "psi"]
-CPLX_FIELDS = ["u_hat", "v_hat", "omega_hat", "psi_hat", "nonlinear_hat", "rk1_hat", "rk2_hat",
-               "rk3_hat", "rk4_hat", "omega_tmp_hat"]
-
-_SPECTRAL_FIELDS = (
-    [("nx", C.c_int), ("ny", C.c_int), ("nkx", C.c_int), ("nky", C.c_int),
-     ("Lx", C.c_double), ("Ly", C.c_double), ("Re", C.c_double), ("dt", C.c_double),
-     ("t", C.c_double), ("cfl_factor", C.c_double)]
-    + [(n, c_double_p) for n in REAL_FIELDS + ["x", "y"]]
-    + [(n, c_double_p) for n in CPLX_FIELDS]
-    + [("kx", c_double_p), ("ky", c_double_p), ("k2", c_double_p),
-       ("forward_plan", C.c_void_p), ("backward_plan", C.c_void_p),
-       ("dealias_mask", c_int_p),
-       ("hyperviscosity", Hyperviscosity),
-       ("hyperviscosity_weights", c_double_p),
-       ("sfd_hat", c_double_p)]
-)
-
-
-class SpectralStruct(C.Structure):
-    _fields_ = _SPECTRAL_FIELDS
-
-
-class ForcingConfig(C.Structure):
-    _fields_ = [("kmin", C.c_double), ("kmax", C.c_double), ("energy_target", C.c_double),
-                ("correlation_time", C.c_double), ("seed", C.c_ulong), ("type", C.c_int)]
-
-
-class ForcingState(C.Structure):
-    _fields_ = [("config", ForcingConfig), ("nkx", C.c_int), ("nky", C.c_int),
-                ("spectral_size", C.c_int), ("active_modes", C.c_int),
-                ("weights", c_double_p), ("colored_state", c_double_p),
-                ("have_spare", C.c_uint), ("spare_gaussian", C.c_double),
-                ("rng_state", C.c_ulonglong)]
+from ns_structs import (CPLX_FIELDS, REAL_FIELDS, ForcingConfig, ForcingState, Hyperviscosity,  # noqa: F401
+                        SpectralStruct, View, _SPECTRAL_FIELDS, c_double_p, c_int_p)
 
 
 def build_oracles():
@@ -78,55 +27,55 @@ def build_oracles():
                    stdout=subprocess.DEVNULL)
 
 
-def lib_path(kind):
-    return os.path.join(ORACLE_DIR, "_ref", "libns_ref.so") if kind == "ref" else \
-        os.path.join(ORACLE_DIR, "libns_oracle.so")
+def lib_path(kind, flavour="parity"):
+    if kind == "ref":
+        v4 = os.path.join(ORACLE_DIR, "_ref", "libns_ref_v4.so")
+        if flavour == "timing" and os.path.exists(v4) and _cpu_has("avx512f"):
+            return v4
+        return os.path.join(ORACLE_DIR, "_ref", "libns_ref.so")
+    return os.path.join(ORACLE_DIR, "libns_oracle.so")
+
+
+def _cpu_has(flag):
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                return flag in line.split()
+    except OSError:
+        pass
+    return False
+
+
+def build_flavour(kind, flavour="timing"):
+    """compiler flags of the library lib_path() selects (for the bench line's provenance text)"""
+    if kind == "ref" and lib_path(kind, flavour).endswith("_v4.so"):
+        return "gcc -O3 -fopenmp -march=x86-64-v4 -ffp-contract=off"
+    return "gcc -O3 -fopenmp -mavx2 -mfma -ffp-contract=off"
+
+
+def set_threads(n):
+    """OMP threads of the oracle libraries. OMP_NUM_THREADS is read once when libgomp initialises, which
+    torch / numpy may already have triggered (and torchrun exports OMP_NUM_THREADS=1), so set it through
+    the runtime as well. Returns the number in effect."""
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        gomp = C.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(int(n))
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return int(n)
 
 
 def have(kind):
     return os.path.exists(lib_path(kind))
 
 
-class View:
-    """numpy views onto the arrays of a (reference-layout) spectral struct."""
-
-    def __init__(self, sp):
-        self.sp = sp
-        s = sp.contents
-        self.nx, self.ny, self.nkx, self.nky = s.nx, s.ny, s.nkx, s.nky
-
-    def real(self, name):
-        s = self.sp.contents
-        return np.ctypeslib.as_array(getattr(s, name), shape=(self.ny, self.nx))
-
-    def cplx(self, name):
-        s = self.sp.contents
-        a = np.ctypeslib.as_array(getattr(s, name), shape=(self.nky, self.nkx * 2))
-        return a.view(np.complex128)
-
-    def vec(self, name, n):
-        return np.ctypeslib.as_array(getattr(self.sp.contents, name), shape=(n,))
-
-    @property
-    def k2(self):
-        return np.ctypeslib.as_array(self.sp.contents.k2, shape=(self.nky, self.nkx))
-
-    @property
-    def mask(self):
-        return np.ctypeslib.as_array(self.sp.contents.dealias_mask, shape=(self.nky, self.nkx))
-
-    @property
-    def weights(self):
-        return np.ctypeslib.as_array(self.sp.contents.hyperviscosity_weights,
-                                     shape=(self.nky, self.nkx))
-
-
 class Oracle:
     """One solver instance on one of the CPU oracles."""
 
-    def __init__(self, kind, nx, ny, Lx=2 * np.pi, Ly=2 * np.pi, Re=100.0, threads=None):
+    def __init__(self, kind, nx, ny, Lx=2 * np.pi, Ly=2 * np.pi, Re=100.0, threads=None, flavour="parity"):
         self.kind = kind
-        self.lib = C.CDLL(lib_path(kind))
+        self.lib = C.CDLL(lib_path(kind, flavour))
         self.pfx = "ns_spectral_" if kind == "ref" else "orc_spectral_"
         self.fpfx = "ns_forcing_" if kind == "ref" else "orc_forcing_"
         L = self.lib

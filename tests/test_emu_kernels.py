@@ -155,6 +155,7 @@ def test_emu_slab_decomposition_two_devices(nsb, emu_lib):
     one.set_hyperviscosity(**HV)
     one.step(0.0)
     ref, dt_ref = one.download(nsb.OMEGA_HAT), one.state()[0]
+    ck_ref = one.state_checksum()
     one.close()
     grp = nsb.NsbGroup(nx, ny, 2, devices=[0, 0], lib=emu_lib, Re=500.0)
     grp.upload(nsb.OMEGA_HAT, w)
@@ -164,9 +165,17 @@ def test_emu_slab_decomposition_two_devices(nsb, emu_lib):
     grp.step(0.0)
     got = grp.download_omega_hat()
     dts = grp.each(lambda c: c.state()[0])
+    sums = grp.each(lambda c: c.state_checksum())
     grp.close()
     assert np.array_equal(got, ref)
     assert dts[0] == dts[1] == dt_ref
+    # nsb_state_checksum: XOR / wrapping sum over the own columns combine to the one-device value
+    assert sums[0][0] ^ sums[1][0] == ck_ref[0] and (sums[0][1] + sums[1][1]) % 2**64 == ck_ref[1]
+    bits = ref[:, :343].copy().view(np.uint64).reshape(ny, 343, 2)
+    re, im = bits[..., 0], bits[..., 1]
+    rot = (im << np.uint64(1)) | (im >> np.uint64(63))
+    assert ck_ref[0] == int(np.bitwise_xor.reduce((re ^ rot).reshape(-1)))
+    assert ck_ref[1] == (int(re.sum(dtype=np.uint64)) + 3 * int(im.sum(dtype=np.uint64))) % 2**64
 
 
 def test_emu_spectral_stats(nsb, emu_lib):

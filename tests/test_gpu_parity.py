@@ -12,6 +12,15 @@ SFD = dict(enabled=1, coefficient=0.5, order=4, cutoff_ratio=0.3, sfd_enabled=1,
            sfd_timescale=0.4)
 
 
+def _block_spectrum(n, kk=64, seed=5):
+    """rows, block: a random Hermitian-consistent low-k block of a n x (n/2+1) spectrum"""
+    rng = np.random.default_rng(seed)
+    blk = rng.standard_normal((2 * kk + 1, kk + 1)) + 1j * rng.standard_normal((2 * kk + 1, kk + 1))
+    blk[kk, 0] = 0.0                                     # the mean mode
+    blk[:, 0] = 0.5 * (blk[:, 0] + np.conj(blk[::-1, 0]))  # kx = 0 column: spectrum of a real field
+    return np.arange(-kk, kk + 1) % n, blk
+
+
 @pytest.mark.parametrize("nx,ny,plan", [
     (32, 32, {}), (64, 32, dict(y1=8, x2=8)), (128, 64, dict(y1=4, x2=8, col_tile=4, beta_batch=4)),
     (256, 256, {}), (512, 256, dict(y1=64, x2=128)), (2048, 2048, {}),
@@ -35,10 +44,87 @@ def test_step_decaying_1024(nsb, cuda_lib, oracles):
     pc.check_per_step(nsb, cuda_lib, oracles, best_oracle_kind(oracles), 1024, 1024, 3, hv=HV, Re=1e4)
 
 
-def test_step_forced_white_split_plan(nsb, cuda_lib, oracles):
-    """the 16384^2 plan (Y2 = X1 = 16) in miniature, forced"""
+def test_step_forced_white_split_plan_generic_kernels(nsb, cuda_lib, oracles):
+    """Y2 = X1 = 16 in miniature on the GENERIC kernels (y1 = x2 = 32 are not the warp-FFT long
+    factors, so this does not touch the fast path; the fast-path instantiations with 16- and
+    32-point short factors are covered by test_step_fast_path_short_factors below)."""
     pc.check_per_step(nsb, cuda_lib, oracles, best_oracle_kind(oracles), 512, 512, 3, hv=HV,
                       forcing=dict(kind="white"), Re=1e4, y1=32, x2=32)
+
+
+@pytest.mark.parametrize("nx,ny,want", [
+    (1024, 16384, (1024, 16, 1, 1024)),    # Y2 = 16: the column kernel + j2 DFT of B/F exactly as at 16384^2
+    (16384, 1024, (1024, 1, 16, 1024)),    # X1 = 16: the k1 DFT / Hermitian gather of B/F exactly as at 16384^2
+    (1024, 32768, (1024, 32, 1, 1024)),    # Y2 = 32: BASELINE config 5's column factorisation
+    (32768, 1024, (1024, 1, 32, 1024)),    # X1 = 32: 22 column segments, packed step 2 of B
+])
+def test_step_fast_path_short_factors(nsb, cuda_lib, oracles, nx, ny, want):
+    """The headline instantiations of the FAST path against oracle/_ref on the GPU: rectangular grids
+    whose long factors are 1024 (k_alpha1024 with TMA tiles, TMA-fed k_chain_B, k_chain_G, k_chain_F)
+    and whose short factor is the 16 / 32 the square 16384^2 / 32768^2 grids use. Forced + hyperviscous,
+    per-step rel-L2(omega_hat) <= 1e-11 (spectral_time_integration.c:34-106 is the loop being matched)."""
+    c = nsb.NsbContext(nx, ny, lib=cuda_lib)
+    p = c.plan()
+    c.close()
+    assert (p["Y1"], p["Y2"], p["X1"], p["X2"]) == want
+    pc.check_per_step(nsb, cuda_lib, oracles, best_oracle_kind(oracles), nx, ny, 2, hv=HV,
+                      forcing=dict(kind="white"), Re=1e4)
+
+
+@pytest.mark.parametrize("nx,ny,plan", [
+    (2048, 64, dict(x2=1024, y1=2)),       # X1 = 2, Y2 = 32: 32-row slabs (the emulator case, on hardware)
+    (32768, 16, dict(x2=1024, y1=4)),      # X1 = 32, Y2 = 4: 4-column TMA boxes of B
+])
+def test_step_chain_32_point_factors_small(nsb, cuda_lib, oracles, nx, ny, plan):
+    pc.check_per_step(nsb, cuda_lib, oracles, best_oracle_kind(oracles), nx, ny, 2, hv=HV,
+                      forcing=dict(kind="white"), Re=1e4, **plan)
+
+
+def test_free_running_config2_1024_1000_steps(nsb, cuda_lib, oracles):
+    """BASELINE config 2 as written: decaying 1024^2, random-phase IC, hyperviscosity, adaptive dt,
+    1000 free-running steps; E and enstrophy within 1e-9 relative (north-star drift bound)."""
+    pc.check_free_running(nsb, cuda_lib, oracles, best_oracle_kind(oracles), 1024, 1024, 1000, every=50, hv=HV,
+                          Re=1e4)
+
+
+def test_step_16384_vs_oracle(nsb, cuda_lib, oracles):
+    """The headline configuration itself (16384^2, Y2 = X1 = 16, forced + hyperviscous) against
+    oracle/_ref for ONE step: the reference needs ~37 GB and ~1 min per step with the shim FFT, so the
+    test runs only where the host has the memory."""
+    import psutil
+    if psutil.virtual_memory().available < 72 * 2**30:
+        pytest.skip("needs ~60 GB of host memory for the 16384^2 oracle")
+    pc.check_per_step(nsb, cuda_lib, oracles, best_oracle_kind(oracles), 16384, 16384, 1, hv=HV,
+                      forcing=dict(kind="white"), Re=1e4)
+
+
+def test_fast_vs_generic_16384(nsb, cuda_lib, monkeypatch):
+    """16384^2: the fast path (1024 x 16 both ways) and the generic kernels (NSB_DISABLE_FAST=1), which
+    share no transform kernel, agree to 1e-11 on omega_hat after two adaptive steps, and on dt, t."""
+    n, kk = 16384, 64
+    rows, blk = _block_spectrum(n, kk)
+    cols = np.arange(kk + 1)
+    res = []
+    for fast in (1, 0):
+        monkeypatch.setenv("NSB_DISABLE_FAST", "0" if fast else "1")
+        c = nsb.NsbContext(n, n, Re=1e4, lib=cuda_lib)
+        w = np.zeros((n, n // 2 + 1), dtype=np.complex128)
+        w[rows[:, None], cols[None, :]] = 0.02 * blk
+        c.upload(nsb.OMEGA_HAT, w)
+        del w
+        c.set_hyperviscosity(**HV)
+        for _ in range(2):
+            c.step(0.0)
+        out = c.download(nsb.OMEGA_HAT)
+        band = out[np.arange(-4 * kk, 4 * kk + 1) % n][:, : 4 * kk + 1].copy()
+        tot = float(np.vdot(out, out).real)
+        del out
+        dt, t, _ = c.state()
+        c.close()
+        res.append((band, tot, dt, t))
+    assert pc.rel(res[1][0], res[0][0]) < 1e-11
+    assert abs(res[1][1] - res[0][1]) <= 1e-11 * res[0][1]
+    assert abs(res[1][2] - res[0][2]) <= 1e-13 * res[0][2] and abs(res[1][3] - res[0][3]) <= 1e-13 * res[0][3]
 
 
 def test_step_forced_colored_sfd(nsb, cuda_lib, oracles):
@@ -91,15 +177,6 @@ def test_large_size_properties_16384(nsb, cuda_lib):
     assert 0 < d1["energy"] < d0["energy"]
     assert 0 < d1["enstrophy"] < d0["enstrophy"]
     c.close()
-
-
-def _block_spectrum(n, kk=64, seed=5):
-    """rows, block: a random Hermitian-consistent low-k block of a n x (n/2+1) spectrum"""
-    rng = np.random.default_rng(seed)
-    blk = rng.standard_normal((2 * kk + 1, kk + 1)) + 1j * rng.standard_normal((2 * kk + 1, kk + 1))
-    blk[kk, 0] = 0.0                                     # the mean mode
-    blk[:, 0] = 0.5 * (blk[:, 0] + np.conj(blk[::-1, 0]))  # kx = 0 column: spectrum of a real field
-    return np.arange(-kk, kk + 1) % n, blk
 
 
 def _chunk_absmax(a, rows=1024):

@@ -299,6 +299,66 @@ def test_lazy_run_steps_gpu(gpu_host, oracles, kind):
     _lazy_run_steps(gpu_host, oracles, kind)
 
 
+def _group_case(lib, n, gpus, case):
+    """one scenario of the reference-facing entry points, on one device or on a device group"""
+    s = hostlib.Solver(lib, n, n, Re=1e4)
+    if gpus > 1:
+        assert lib.ns_spectral_backend_init(s.sp, gpus) == 0, lib.ns_spectral_last_error()
+    lib.ns_spectral_initialize_random_phase(s.sp, 11, 8.0, 5.0)
+    h = orc.Hyperviscosity()
+    lib.ns_spectral_hyperviscosity_default(C.byref(h))
+    h.enabled, h.coefficient, h.order, h.cutoff_ratio = 1, 5.0, 4, 0.3
+    lib.ns_spectral_hyperviscosity_set(s.sp, C.byref(h))
+    out = {}
+    if case == "eager_loop":
+        # the reference driver loop (main_spectral.c:46-48) under NS_SYNC_EAGER
+        for _ in range(2):
+            s.s.dt = lib.ns_spectral_compute_cfl_timestep(s.sp)
+            lib.ns_spectral_advance_rk4(s.sp)
+        out["dt"], out["t"] = s.s.dt, s.s.t
+    elif case == "lazy_sfd_after_steps":
+        lib.ns_spectral_set_sync_policy(s.sp, 1)
+        assert lib.ns_spectral_run_steps(s.sp, 2, None) == 0
+        h.sfd_enabled, h.sfd_strength, h.sfd_timescale = 1, 0.3, 0.05
+        lib.ns_spectral_hyperviscosity_set(s.sp, C.byref(h))      # seeds sfd_hat from the CURRENT omega_hat
+        assert lib.ns_spectral_run_steps(s.sp, 2, None) == 0
+        out["cfl"] = lib.ns_spectral_compute_cfl_timestep(s.sp)   # gathered single-device call on a group
+        lib.ns_spectral_sync_to_host(s.sp, 0xFFFFFFFF)
+        out["dt"], out["t"] = s.s.dt, s.s.t
+        out["sfd"] = np.array(s.arr("sfd_hat"))
+        assert np.linalg.norm(out["sfd"]) > 0
+    else:  # coloured forcing: the CFL step is needed on the host before every step
+        cfg = orc.ForcingConfig()
+        lib.ns_forcing_config_default(C.byref(cfg))
+        cfg.kmin, cfg.kmax, cfg.energy_target, cfg.correlation_time, cfg.seed, cfg.type = 0.5, 4.0, 1.25, 0.4, 42, 1
+        fs = orc.ForcingState()
+        assert lib.ns_forcing_state_init(C.byref(fs), C.byref(cfg), s.s.k2, s.s.nkx, s.s.nky) == 0
+        lib.ns_spectral_set_sync_policy(s.sp, 1)
+        assert lib.ns_spectral_run_steps(s.sp, 3, C.byref(fs)) == 0, lib.ns_spectral_last_error()
+        lib.ns_spectral_sync_to_host(s.sp, 0xFFFFFFFF)
+        out["dt"], out["t"], out["rng"] = s.s.dt, s.s.t, fs.rng_state
+        lib.ns_forcing_state_free(C.byref(fs))
+    out["w"] = np.array(s.arr("omega_hat"))
+    s.close()
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["eager_loop", "lazy_sfd_after_steps", "colored_forcing"])
+def test_device_group_entry_points_gpu(gpu_host, monkeypatch, case):
+    """Every entry point on a slab-decomposed device group (ns_spectral_backend_init, here 2 logical devices
+    on GPU 0) must reproduce the single-device run bit for bit: the reference driver loop cfl + advance_rk4
+    (EAGER), enabling the SFD filter after LAZY steps, and coloured forcing through ns_spectral_run_steps."""
+    monkeypatch.setenv("NS_SPECTRAL_GROUP_SAME_DEVICE", "1")
+    one = _group_case(gpu_host, 2048, 1, case)
+    grp = _group_case(gpu_host, 2048, 2, case)
+    for k in one:
+        if isinstance(one[k], np.ndarray):
+            assert np.array_equal(one[k], grp[k]), k
+        else:
+            assert one[k] == grp[k], k
+
+
 @pytest.mark.gpu
 def test_cli_runs_with_config_files(cuda_lib, tmp_path):
     """README.md:67-77 usage: repeated --config, later files override."""
@@ -313,6 +373,22 @@ def test_cli_runs_with_config_files(cuda_lib, tmp_path):
     assert "Resolution: 128x64 modes" in out.stdout
     assert "=== SIMULATION COMPLETED ===" in out.stdout
     assert "Step 10:" in out.stdout
+
+
+@pytest.mark.gpu
+def test_cli_honours_intervals_that_are_not_multiples_of_ten(cuda_lib, tmp_path):
+    """output.interval = 7 and restart.interval = 4: the loop advances in batches but must stop at every
+    multiple of both (the reference tests `step % interval == 0` after each step, main_spectral.c:51-64)."""
+    ini = tmp_path / "c.ini"
+    ini.write_text("[grid]\nnx = 64\nny = 64\n[fluid]\nRe = 100.0\n[time]\nt_end = 100.0\nmax_steps = 23\n"
+                   "[output]\ninterval = 7\nprefix = snap\n[restart]\nsave = r.bin\ninterval = 4\n")
+    exe = os.path.join(ROOT, "navier-stokes-solvers_b200", "bin", "ns_spectral_solver")
+    out = subprocess.run([exe, "--config", str(ini)], capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert out.returncode == 0, out.stderr
+    snaps = sorted(p.name for p in tmp_path.glob("snap_step_*.dat"))
+    assert snaps == ["snap_step_0007.dat", "snap_step_0014.dat", "snap_step_0021.dat"]
+    assert "Step 10:" in out.stdout and "Step 20:" in out.stdout
+    assert (tmp_path / "r.bin").exists()
 
 
 @pytest.mark.gpu
