@@ -961,9 +961,6 @@ struct AlphaFastArgs {
     NsbRk rk;        /* K-layout pointers */
 };
 
-/* modes per thread and round of the RK sweep: all their state loads are in flight together (the
- * transform registers are idle during the sweep, so there is room for 8 x 3 complex values) */
-#ifndef NSB_RK_BATCH
 /* tensor maps of the T buffer of every device (3-D: {2*PT doubles, Y2, 4 fields x own y1 rows},
  * 128B swizzle) for the TMA tile stores of k_alpha1024<.., TMA = true> */
 struct NsbTmaps {
@@ -971,7 +968,15 @@ struct NsbTmaps {
     nsb_tmap tp; /* the local T' buffer: {2*cb doubles, Y2, Y1}, for the TMA load of the forward tile */
 };
 
-#define NSB_RK_BATCH 4 /* measured: 8 (and telling the allocator x is dead during the sweep) is 20 % slower */
+/* modes per lane whose RK state loads are in flight together in the in-register RK update of
+ * k_alpha1024 (the transform registers stay live, so there is room for about 4 x 3 complex values) */
+#ifndef NSB_RK_BATCH
+#define NSB_RK_BATCH 4
+#endif
+/* 1: fully unrolled update on the live transform registers; 2 (default): rolled, double-buffered loop
+ * with the values parked in the lane's own tile slots */
+#ifndef NSB_RK_MODE
+#define NSB_RK_MODE 2
 #endif
 #ifndef NSB_TILE_UNROLL
 #define NSB_TILE_UNROLL 8
@@ -1128,6 +1133,118 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
             if (TMA) nsb_fft1024_warp_sw<true>(x, TS, TW, lane);
             else nsb_fft1024_warp_col<true, COLS>(x, S, warp, TW, lane);
         }
+        if (job == 0) {
+            /* RK update in registers: after the forward transform lane t holds N_hat of rows j1 = t + 32 m of
+             * its own column, and the K-layout state of that column is contiguous in j1, so every lane updates
+             * its own 32 modes against 512-byte coalesced loads -- no tile round trip, no block barrier, and the
+             * new stage state stays in x for the first inverse job. (Round 1 swept the tile with all threads
+             * after a barrier: a third of this kernel's stall samples, profiles/README.md round 2.) */
+#if NSB_RK_MODE == 1
+            if (active) {
+                const double dt = *a.rk.dt;
+                const bool use_sfd = a.rk.hv.sfd != 0;
+#pragma unroll
+                for (int m0 = 0; m0 < 32; m0 += NSB_RK_BATCH) {
+                    cd W0v[NSB_RK_BATCH], Wsv[NSB_RK_BATCH], ACv[NSB_RK_BATCH], SFv[NSB_RK_BATCH];
+#pragma unroll
+                    for (int u = 0; u < NSB_RK_BATCH; ++u) {
+                        const size_t kid = kbase + lane + 32 * (m0 + u);
+                        W0v[u] = a.rk.W0[kid];
+                        Wsv[u] = (a.rk.stage == 1) ? W0v[u] : a.rk.Wst[kid];
+                        ACv[u] = (a.rk.stage == 1) ? cmk(0.0, 0.0) : a.rk.ACC[kid];
+                        SFv[u] = use_sfd ? a.rk.SFD[kid] : cmk(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < NSB_RK_BATCH; ++u) {
+                        const int m = m0 + u;
+                        const int j1 = lane + 32 * m;
+                        const size_t kid = kbase + j1;
+                        cd nxt = cmk(0.0, 0.0);
+                        if ((keepmask >> m) & 1u) {
+                            /* x holds the conjugate of the forward transform (forward = conj o inverse o conj) */
+                            const cd Nh = cmk(-(x[m].x * g.norm), x[m].y * g.norm);
+                            cd acc, sfd;
+                            nxt = nsb_rk_math(a.rk, dt, W0v[u], Wsv[u], ACv[u], SFv[u], kxv, KY[j1], ic,
+                                              nsb_band(j1 * g.Y2 + j2, g.ny), Nh, &acc, &sfd);
+                            if (a.rk.stage < 4) {
+                                a.rk.ACC[kid] = acc;
+                                a.rk.Wst[kid] = nxt;
+                            } else {
+                                a.rk.W0[kid] = nxt;
+                                if (use_sfd) a.rk.SFD[kid] = sfd;
+                            }
+                        }
+                        x[m] = nxt; /* rows the mask removes get the factor 0 in the inverse jobs */
+                    }
+                }
+                prefetched = true;
+            }
+#else
+            /* The lane parks its 32 values in its own slots of the tile (it reads back only what it wrote
+             * itself: no synchronisation) so that the transform registers are free and the update loop can
+             * stay rolled: small code, room for the NEXT batch's state loads to be in flight while the current
+             * batch is computed. The new stage state goes back into the same slots for the first inverse job. */
+            if (active) {
+                const double dt = *a.rk.dt;
+                const bool use_sfd = a.rk.hv.sfd != 0;
+#pragma unroll
+                for (int m = 0; m < 32; ++m) S[nsb_sidx<COLS>(lane + 32 * m, warp)] = x[m];
+                cd W0v[2][NSB_RK_BATCH], Wsv[2][NSB_RK_BATCH], ACv[2][NSB_RK_BATCH], SFv[2][NSB_RK_BATCH];
+                auto fetch = [&](int buf, int m0) {
+#pragma unroll
+                    for (int u = 0; u < NSB_RK_BATCH; ++u) {
+                        const size_t kid = kbase + lane + 32 * (m0 + u);
+                        W0v[buf][u] = a.rk.W0[kid];
+                        Wsv[buf][u] = (a.rk.stage == 1) ? W0v[buf][u] : a.rk.Wst[kid];
+                        ACv[buf][u] = (a.rk.stage == 1) ? cmk(0.0, 0.0) : a.rk.ACC[kid];
+                        SFv[buf][u] = use_sfd ? a.rk.SFD[kid] : cmk(0.0, 0.0);
+                    }
+                };
+                auto update = [&](int buf, int m0) {
+#pragma unroll
+                    for (int u = 0; u < NSB_RK_BATCH; ++u) {
+                        const int m = m0 + u;
+                        const int j1 = lane + 32 * m;
+                        const size_t kid = kbase + j1;
+                        cd *slot = &S[nsb_sidx<COLS>(j1, warp)];
+                        cd nxt = cmk(0.0, 0.0);
+                        if ((keepmask >> m) & 1u) {
+                            const cd v = *slot; /* conjugate of the forward transform */
+                            const cd Nh = cmk(-(v.x * g.norm), v.y * g.norm);
+                            cd acc, sfd;
+                            nxt = nsb_rk_math(a.rk, dt, W0v[buf][u], Wsv[buf][u], ACv[buf][u], SFv[buf][u], kxv, KY[j1],
+                                              ic, nsb_band(j1 * g.Y2 + j2, g.ny), Nh, &acc, &sfd);
+                            if (a.rk.stage < 4) {
+                                a.rk.ACC[kid] = acc;
+                                a.rk.Wst[kid] = nxt;
+                            } else {
+                                a.rk.W0[kid] = nxt;
+                                if (use_sfd) a.rk.SFD[kid] = sfd;
+                            }
+                        }
+                        if (INV) *slot = nxt; /* rows the mask removes get the factor 0 in the inverse jobs */
+                    }
+                };
+                fetch(0, 0);
+#pragma unroll 1
+                for (int m0 = 0; m0 < 32; m0 += 2 * NSB_RK_BATCH) {
+                    fetch(1, m0 + NSB_RK_BATCH);
+                    update(0, m0);
+                    if (m0 + 2 * NSB_RK_BATCH < 32) fetch(0, m0 + 2 * NSB_RK_BATCH);
+                    update(1, m0 + NSB_RK_BATCH);
+                }
+                if (INV) {
+#pragma unroll
+                    for (int m = 0; m < 32; ++m) x[m] = S[nsb_sidx<COLS>(lane + 32 * m, warp)];
+                    prefetched = true;
+                }
+            }
+            /* the next transform's transpose (LDG/STG variant: through this column of the tile) writes slots
+             * of OTHER lanes: every lane must be done with its parked values first */
+            __syncwarp();
+#endif
+            continue; /* every warp touched only its own column of the tile: no barrier */
+        }
         if (TMA && job >= 2) {
             /* the tile store of the previous job ran behind this transform; it must have finished
              * READING the tile before the tile is overwritten */
@@ -1135,71 +1252,23 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
             __syncthreads();
         }
         if (active) {
-            if (job == 0) {
 #pragma unroll
-                for (int m = 0; m < 32; ++m) S[nsb_sidx<COLS>(lane + 32 * m, warp)] = cmk(x[m].x, -x[m].y);
-            } else {
+            for (int m = 0; m < 32; ++m) {
+                cd v = x[m];
+                if (g.Y2 > 1) v = cmulc(v, cmul(ta, TB[m]));
+                S[nsb_sidx<COLS>(lane + 32 * m, warp)] = v;
+            }
+            /* registers are free until the next transform: fetch its input now so the
+             * latency hides behind the barrier and the cooperative store of this tile */
+            if (job < 4) {
 #pragma unroll
-                for (int m = 0; m < 32; ++m) {
-                    cd v = x[m];
-                    if (g.Y2 > 1) v = cmulc(v, cmul(ta, TB[m]));
-                    S[nsb_sidx<COLS>(lane + 32 * m, warp)] = v;
-                }
-                /* registers are free until the next transform: fetch its input now so the
-                 * latency hides behind the barrier and the cooperative store of this tile */
-                if (job < 4) {
-#pragma unroll
-                    for (int m = 0; m < 32; ++m) x[m] = Wre[kbase + lane + 32 * m];
-                    prefetched = true;
-                }
+                for (int m = 0; m < 32; ++m) x[m] = Wre[kbase + lane + 32 * m];
+                prefetched = true;
             }
         }
-        if (TMA && job >= 1) nsb_fence_proxy_async(); /* generic-proxy tile writes -> visible to the TMA store */
+        if (TMA) nsb_fence_proxy_async(); /* generic-proxy tile writes -> visible to the TMA store */
         __syncthreads();
-        if (job == 0) {
-            /* RK sweep: thread takes elements flat = tid + 32*COLS*i of the COLS x 1024 tile, four at a
-             * time with all state loads issued before the arithmetic */
-            const double dt = *a.rk.dt;
-            const bool use_sfd = a.rk.hv.sfd != 0;
-#pragma unroll 1
-            for (int i0 = 0; i0 < 32; i0 += NSB_RK_BATCH) {
-                cd W0v[NSB_RK_BATCH], Wsv[NSB_RK_BATCH], ACv[NSB_RK_BATCH], SFv[NSB_RK_BATCH];
-                size_t kid[NSB_RK_BATCH];
-#pragma unroll
-                for (int u = 0; u < NSB_RK_BATCH; ++u) {
-                    const int flat = threadIdx.x + (32 * COLS) * (i0 + u);
-                    const int c = flat >> 10, j1 = flat & 1023;
-                    int icc = ic0 + c;
-                    if (icc >= a.c1) icc = a.c1 - 1; /* clamped: loaded, never stored */
-                    kid[u] = ((size_t)(icc - a.c0) * g.Y2 + j2) * 1024 + j1;
-                    W0v[u] = a.rk.W0[kid[u]];
-                    Wsv[u] = (a.rk.stage == 1) ? W0v[u] : a.rk.Wst[kid[u]];
-                    ACv[u] = (a.rk.stage == 1) ? cmk(0.0, 0.0) : a.rk.ACC[kid[u]];
-                    SFv[u] = use_sfd ? a.rk.SFD[kid[u]] : cmk(0.0, 0.0);
-                }
-#pragma unroll
-                for (int u = 0; u < NSB_RK_BATCH; ++u) {
-                    const int flat = threadIdx.x + (32 * COLS) * (i0 + u);
-                    const int c = flat >> 10, j1 = flat & 1023;
-                    const int icc = ic0 + c;
-                    const int band = nsb_band(j1 * g.Y2 + j2, g.ny);
-                    if (icc < a.c1 && nsb_iabs(band) <= g.ycut) {
-                        const cd v = S[nsb_sidx<COLS>(j1, c)];
-                        const cd Nh = cmk(-(v.x * g.norm), -(v.y * g.norm));
-                        cd acc, sfd;
-                        const cd nxt = nsb_rk_math(a.rk, dt, W0v[u], Wsv[u], ACv[u], SFv[u], __ldg(&g.kx[icc]), KY[j1],
-                                                   icc, band, Nh, &acc, &sfd);
-                        if (a.rk.stage < 4) {
-                            a.rk.ACC[kid[u]] = acc;
-                            a.rk.Wst[kid[u]] = nxt;
-                        } else {
-                            a.rk.W0[kid[u]] = nxt;
-                            if (use_sfd) a.rk.SFD[kid[u]] = sfd;
-                        }
-                    }
-                }
-            }
-        } else if (TMA) {
+        if (TMA) {
             /* one thread hands the whole tile to the TMA unit: 1024 / tma_br boxes of tma_br rows x 8
              * columns, each to the device that owns those rows; no barrier, the next transform starts */
             if (threadIdx.x == 0) {
