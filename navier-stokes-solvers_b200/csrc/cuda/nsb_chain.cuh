@@ -54,6 +54,7 @@ struct ChainArgs {
     int nd, nm;  /* direct / mirror column segments (nsb_beta_segs) */
     unsigned long long *umax_bits;
     /* persistent mode */
+    NsbFastDiv fd_perg, fd_nb, fd_nb2; /* TMA-fed B: divisions by nseg*BC, nbatch, 2*nbatch */
     unsigned *ctr; /* [0] ticket, [1 + s] doneB, [1 + nslab + s] doneG, [1 + 2 nslab + s] doneF */
     int leadG, leadF;
 };
@@ -385,11 +386,13 @@ __device__ __forceinline__ void chain_seg_range(const NsbGeom &g, int nd, int se
  * zeros or as neighbouring retained columns; step 1 masks them by range. Completion on `bar`.
  */
 __device__ __forceinline__ void chain_B_issue(const NsbGeom &g, const ChainArgs &a, const nsb_tmap *tmT, cd *tile,
-                                              nsb_mbar_t *bar, int slab, int pp, int kb) {
+                                              cd *twtab, nsb_mbar_t *bar, int slab, int pp, int kb) {
     const int nseg = a.nd + a.nm;
     if (threadIdx.x == 0) {
         nsb_fence_proxy_async();
-        nsb_mbar_expect_tx(bar, (unsigned)(2 * nseg) * (unsigned)(a.R * g.BC * 16));
+        nsb_mbar_expect_tx(bar, (unsigned)(2 * nseg) * (unsigned)(a.R * g.BC * 16) + (unsigned)(g.BC * g.X1 * 16));
+        /* the x twiddles of this k2 batch: one contiguous block of the batch-ordered table */
+        nsb_bulk_g2s(twtab, g.TWK + (size_t)kb * g.X1, (unsigned)(g.BC * g.X1 * 16), bar);
     }
     __syncthreads();
     if ((int)threadIdx.x < 2 * nseg) {
@@ -406,12 +409,13 @@ template <int Y2>
 __device__ __forceinline__ void chain_B2_step1(const NsbGeom &g, const ChainArgs &a, cd *tile, int kb) {
     const int nseg = a.nd + a.nm;
     const int per_g = nseg * g.BC, per_f = a.GY * per_g;
+    const int bcs = nsb_log2i(g.BC);
     for (int w = threadIdx.x; w < 2 * per_f; w += blockDim.x) {
-        const int fi = w / per_f;
+        const int fi = w >= per_f ? 1 : 0;
         int r = w - fi * per_f;
-        const int gy = r / per_g;
+        const int gy = (int)nsb_fastdiv((unsigned)r, a.fd_perg);
         r -= gy * per_g;
-        const int seg = r / g.BC, pos = r - seg * g.BC;
+        const int seg = r >> bcs, pos = r & (g.BC - 1);
         int p0, cnt, c0;
         chain_seg_range(g, a.nd, seg, kb, &p0, &cnt, &c0);
         cd *col = tile + (size_t)((fi * nseg + seg) * a.R + gy * Y2) * g.BC + pos;
@@ -453,8 +457,9 @@ template <int X1, bool MO>
 __device__ __forceinline__ void chain_B_step2x(const NsbGeom &g, const ChainArgs &a, const cd *tile, int slot, int pp,
                                                int kb, const cd *twtab) {
     const int nseg = a.nd + a.nm;
+    const int bcs = nsb_log2i(g.BC);
     for (int w = threadIdx.x; w < a.R * g.BC; w += blockDim.x) {
-        const int r = w / g.BC, cc = w - r * g.BC;
+        const int r = w >> bcs, cc = w & (g.BC - 1);
         const int k2 = kb + cc;
         if (k2 > g.X2h) continue;
         cd A[X1], B[X1];
@@ -513,7 +518,7 @@ __device__ __forceinline__ void chain_B_step2p(const NsbGeom &g, const ChainArgs
         const int nitem = a.R * g.BC;
         const int half = special_batch ? (w & 1) : (w >= nitem ? 1 : 0);
         const int item = special_batch ? (w >> 1) : (w - half * nitem);
-        const int r = item / g.BC, cc = item - r * g.BC;
+        const int r = item >> nsb_log2i(g.BC), cc = item & (g.BC - 1);
         const int k2 = kb + cc;
         const bool valid = k2 <= g.X2h;
         const double sg = half ? -1.0 : 1.0;
@@ -577,7 +582,8 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
     const int nseg = a.nd + a.nm;
     const size_t tile_elems = (size_t)2 * a.R * nseg * g.BC;
     nsb_mbar_t *bars = reinterpret_cast<nsb_mbar_t *>(smem + 2 * tile_elems);
-    cd *twtab = smem + 2 * tile_elems + 4; /* BC * X1 x twiddles of the current batch */
+    cd *twtabs = smem + 2 * tile_elems + 4; /* 2 stages x BC * X1 x twiddles (TMA bulk copies, with the tile) */
+    const size_t tw_elems = (size_t)g.BC * g.X1;
     if (threadIdx.x == 0) {
         nsb_mbar_init(&bars[0], 1);
         nsb_mbar_init(&bars[1], 1);
@@ -586,28 +592,33 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
     const int nitems = a.nslab * 2 * a.nbatch;
     unsigned phase[2] = {0u, 0u};
     int item = blockIdx.x;
+    auto decode = [&](int it, int *slab, int *pp, int *kb) {
+        const int sl = (int)nsb_fastdiv((unsigned)it, a.fd_nb2), rem = it - sl * 2 * a.nbatch;
+        const int p = (int)nsb_fastdiv((unsigned)rem, a.fd_nb);
+        *slab = a.slab0 + sl;
+        *pp = p;
+        *kb = (rem - p * a.nbatch) * g.BC;
+    };
     if (item < nitems) {
-        const int sl = item / (2 * a.nbatch), rem = item - sl * 2 * a.nbatch;
-        chain_B_issue(g, a, &tmT, smem, &bars[0], a.slab0 + sl, rem / a.nbatch, (rem % a.nbatch) * g.BC);
+        int slab, pp, kb;
+        decode(item, &slab, &pp, &kb);
+        chain_B_issue(g, a, &tmT, smem, twtabs, &bars[0], slab, pp, kb);
     }
     for (int n = 0; item < nitems; ++n, item += gridDim.x) {
         const int st = n & 1;
         const int next = item + gridDim.x;
         if (next < nitems) {
-            const int sl = next / (2 * a.nbatch), rem = next - sl * 2 * a.nbatch;
-            chain_B_issue(g, a, &tmT, smem + (size_t)(st ^ 1) * tile_elems, &bars[st ^ 1], a.slab0 + sl, rem / a.nbatch,
-                          (rem % a.nbatch) * g.BC);
+            int slab, pp, kb;
+            decode(next, &slab, &pp, &kb);
+            chain_B_issue(g, a, &tmT, smem + (size_t)(st ^ 1) * tile_elems, twtabs + (size_t)(st ^ 1) * tw_elems,
+                          &bars[st ^ 1], slab, pp, kb);
         }
         nsb_mbar_wait(&bars[st], phase[st]);
         phase[st] ^= 1u;
         cd *tile = smem + (size_t)st * tile_elems;
-        const int sl = item / (2 * a.nbatch), rem = item - sl * 2 * a.nbatch;
-        const int slab = a.slab0 + sl;
-        const int pp = rem / a.nbatch, kb = (rem % a.nbatch) * g.BC;
-        for (int w = threadIdx.x; w < g.BC * g.X1; w += blockDim.x) {
-            const int cc = w / g.X1, x1 = w - cc * g.X1;
-            twtab[w] = (kb + cc <= g.X2h) ? __ldg(&g.WX[(size_t)(kb + cc) * x1]) : cmk(1.0, 0.0);
-        }
+        const cd *twtab = twtabs + (size_t)st * tw_elems;
+        int slab, pp, kb;
+        decode(item, &slab, &pp, &kb);
         switch (g.Y2) {
             case 1: chain_B2_step1<1>(g, a, tile, kb); break;
             case 2: chain_B2_step1<2>(g, a, tile, kb); break;
@@ -688,6 +699,127 @@ __global__ void __launch_bounds__(256, 1) k_chain_Gp(NsbGeom g, ChainArgs a) {
         for (int off = 16; off > 0; off >>= 1) umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, off));
         if (lane == 0) atomicMax(a.umax_bits, (unsigned long long)__double_as_longlong(umax));
     }
+}
+
+
+/*
+ * G with tensor-memory parking and TMA-fed inputs (the default on hardware). Same arithmetic as chain_G_pair
+ * (bit-identical results), different data movement:
+ *   - persistent, one CTA per SM, 8 independent warps (no block barrier after start-up), also with UMAX
+ *     (the shared-memory version had room for 6 warps there);
+ *   - every 16 KB comb spectrum is fetched by ONE cp.async.bulk into the warp's landing buffer, signalled on the
+ *     warp's mbarrier; the fetch of input n+1 is issued as soon as input n sits in registers, so it flies during
+ *     the whole transform of input n (round 1: 35-40 % of G's stall samples were global-load waits / LSU throttle
+ *     behind 32 back-to-back LDG.128 per lane);
+ *   - the per-lane values that must survive a register-resident transform (Re*Im products, the Jacobian of comb 0,
+ *     psi_x for max|u|) are parked in TENSOR MEMORY (tcgen05.st / tcgen05.ld, 192 of the warp's 256 columns), not
+ *     in 16-24 KB of shared memory per warp -- which is what makes room for the landing buffers.
+ */
+#define NSB_CHG2_WARP_BYTES (16384 + 8192)
+#define NSB_CHG2_SMEM (NSB_CH_TW_BYTES + 8 * NSB_CHG2_WARP_BYTES + 8 * 8 + 16)
+
+template <bool UMAX>
+__global__ void __launch_bounds__(256, 1) k_chain_G2(NsbGeom g, ChainArgs a) {
+    NSB_DYN_SMEM(unsigned char, raw);
+    cd *TW = reinterpret_cast<cd *>(raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wb = raw + NSB_CH_TW_BYTES + (size_t)warp * NSB_CHG2_WARP_BYTES;
+    cd *L = reinterpret_cast<cd *>(wb);
+    double *T = reinterpret_cast<double *>(wb + 16384);
+    nsb_mbar_t *bars = reinterpret_cast<nsb_mbar_t *>(raw + NSB_CH_TW_BYTES + 8 * NSB_CHG2_WARP_BYTES);
+    unsigned *tslot = reinterpret_cast<unsigned *>(bars + 8);
+    nsb_mbar_t *bar = &bars[warp];
+    nsb_fill_tw1024(TW, g.TWX);
+    if (lane == 0) nsb_mbar_init(bar, 1);
+    const unsigned tbase = nsb_tmem_alloc_all(tslot); /* block barrier inside: TW, mbarriers, TMEM ready */
+    /* this warp's 256 columns: [0,64) J of comb 0 | [64,128) Re*Im of the current comb | [128,192) psi_x */
+    const unsigned tcol = nsb_tmem_warp_base(tbase, warp, (warp >> 2) * 256);
+    /* pairs per slab NP = NQ / 2 is a power of two; one launch covers at most 2^17 pairs; the plain chain keeps
+     * every slab in its own Z / P slot (nslotZ == nslotP == number of slabs of the device) */
+    const int NP = a.NQ >> 1, nps = nsb_log2i(NP);
+    const int total = a.nslab * NP, stride = (int)gridDim.x * 8;
+    auto zsrc = [&](int q, int comb, int pp) -> const cd * {
+        const int slab = a.slab0 + (q >> nps), pair = q & (NP - 1);
+        return a.Z + ((size_t)(slab * 2 + pp) * a.NQ + 2 * pair + comb) * 1024;
+    };
+    auto issue = [&](const cd *src) {
+        if (lane == 0) {
+            nsb_fence_proxy_async();
+            nsb_mbar_expect_tx(bar, 16384u);
+            nsb_bulk_g2s(L, src, 16384u, bar);
+        }
+    };
+    unsigned phase = 0u;
+    int p = (int)blockIdx.x * 8 + warp;
+    if (p < total) issue(zsrc(p, 0, 0));
+    double umax = 0.0;
+    for (; p < total; p += stride) {
+        cd x[32];
+#pragma unroll 1
+        for (int comb = 0; comb < 2; ++comb) {
+            nsb_mbar_wait(bar, phase);
+            phase ^= 1u;
+#pragma unroll
+            for (int m = 0; m < 32; ++m) x[m] = L[lane + 32 * m];
+            __syncwarp(); /* every lane has its values: the landing buffer may be refilled */
+            issue(zsrc(p, comb, 1));
+            nsb_fft1024_warp_sw<true>(x, T, TW, lane); /* x = psi_x + i omega_y */
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                double t[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t[i] = __dmul_rn(x[8 * h + i].x, x[8 * h + i].y);
+                nsb_tmem_st8(tcol + 64 + 16 * h, t);
+                if (UMAX) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) t[i] = x[8 * h + i].x;
+                    nsb_tmem_st8(tcol + 128 + 16 * h, t);
+                }
+            }
+            nsb_tmem_wait_st();
+            nsb_mbar_wait(bar, phase);
+            phase ^= 1u;
+#pragma unroll
+            for (int m = 0; m < 32; ++m) x[m] = L[lane + 32 * m];
+            __syncwarp();
+            if (comb == 0) issue(zsrc(p, 1, 0));
+            else if (p + stride < total) issue(zsrc(p + stride, 0, 0));
+            nsb_fft1024_warp_sw<true>(x, T, TW, lane); /* x = psi_y + i omega_x */
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                double t[8], j[8];
+                nsb_tmem_ld8(t, tcol + 64 + 16 * h);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) /* spectral_core.c:103 : J = psi_x*omega_y - psi_y*omega_x */
+                    j[i] = __dsub_rn(t[i], __dmul_rn(x[8 * h + i].x, x[8 * h + i].y));
+                if (UMAX) { /* spectral_time_integration.c:16 : |u|^2 = psi_y^2 + psi_x^2 */
+                    nsb_tmem_ld8(t, tcol + 128 + 16 * h);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        umax = fmax(umax, __dadd_rn(__dmul_rn(x[8 * h + i].x, x[8 * h + i].x), __dmul_rn(t[i], t[i])));
+                }
+                if (comb == 0) {
+                    nsb_tmem_st8(tcol + 16 * h, j);
+                } else {
+                    nsb_tmem_ld8(t, tcol + 16 * h);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[8 * h + i] = cmk(t[i], j[i]);
+                }
+            }
+            nsb_tmem_wait_st();
+        }
+        nsb_fft1024_warp_sw<false>(x, T, TW, lane);
+        cd *po = a.P + ((size_t)(a.slab0 + (p >> nps)) * NP + (p & (NP - 1))) * 1024;
+#pragma unroll
+        for (int m = 0; m < 32; ++m) po[lane + 32 * m] = x[m];
+    }
+    if (UMAX) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, off));
+        if (lane == 0) atomicMax(a.umax_bits, (unsigned long long)__double_as_longlong(umax));
+    }
+    __syncthreads(); /* every warp is done with tensor memory */
+    nsb_tmem_free_all(tbase);
 }
 
 /* grid (nbatch, nslab) */

@@ -55,7 +55,7 @@ struct nsb_ctx {
     cd *bufA, *bufB;
     size_t buf_elems;
     double *d_kx, *d_ky, *d_kyK;
-    cd *d_WY, *d_WX, *d_TW;
+    cd *d_WY, *d_WX, *d_TW, *d_TWK;
     NsbScalars *d_sc;
     NsbScalars *h_sc; /* pinned */
     NsbHv hv;
@@ -89,6 +89,7 @@ struct nsb_ctx {
     int tmT_ok, tmT8_ok;
     int ch_bbc;
     int ch_gpersist;
+    int ch_g2; /* G with TMEM parking + TMA-fed inputs (k_chain_G2) */
     int ch_pieces;          /* slab ranges of the chain run on two streams (1 = one range, one stream) */
     cudaStream_t stream2;
     cd *bufP;               /* P of the split chain */
@@ -276,6 +277,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->ch_fbc = env_int("NSB_CHAIN_FBC", 0);
     c->ch_fthreads = env_int("NSB_CHAIN_FTHREADS", 128) == 256 ? 256 : 128; /* F with 32-point factors only */
     c->ch_pieces = env_int("NSB_CHAIN_PIECES", 0);         /* 0 = automatic */
+    c->ch_g2 = env_int("NSB_CHAIN_G2", 1);
     c->ch_gpersist = env_int("NSB_CHAIN_GPERSIST", 0); /* measured: the persistent G is 6 % slower (2.93 vs 2.77 ms) */
     c->alpha_cols = env_int("NSB_ALPHA_COLS", 4) == 8 ? 8 : 4;
     c->alpha_tma = env_int("NSB_ALPHA_TMA", 1);
@@ -351,6 +353,19 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
         g.TWX = c->d_TW + 1024;
     }
 
+    {
+        /* the B kernel's x twiddles in the order its batches consume them (entries of the same table) */
+        std::vector<cd> wx, twk;
+        fill_twiddles(wx, g.nx);
+        const int nk2 = ((g.X2h + 1 + 15) / 16) * 16;
+        twk.assign((size_t)nk2 * g.X1, make_double2(1.0, 0.0));
+        for (int k2 = 0; k2 <= g.X2h; ++k2)
+            for (int x1 = 0; x1 < g.X1; ++x1) twk[(size_t)k2 * g.X1 + x1] = wx[((size_t)k2 * x1) % g.nx];
+        CK(cudaMalloc((void **)&c->d_TWK, twk.size() * sizeof(cd)));
+        CK(cudaMemcpy(c->d_TWK, twk.data(), twk.size() * sizeof(cd), cudaMemcpyHostToDevice));
+        g.TWK = c->d_TWK;
+    }
+
     CK(cudaMalloc((void **)&c->d_sc, sizeof(NsbScalars)));
     CK(cudaMemset(c->d_sc, 0, sizeof(NsbScalars)));
     c->mg_sc[0] = c->d_sc;
@@ -393,7 +408,7 @@ extern "C" void nsb_ctx_destroy(nsb_ctx *c) {
     if (c->chZ) cudaFree(c->chZ);
     if (c->chP) cudaFree(c->chP);
     if (c->chCtr) cudaFree(c->chCtr);
-    cudaFree(c->d_kx); cudaFree(c->d_ky); cudaFree(c->d_kyK); cudaFree(c->d_WY); cudaFree(c->d_WX); cudaFree(c->d_TW);
+    cudaFree(c->d_kx); cudaFree(c->d_ky); cudaFree(c->d_kyK); cudaFree(c->d_WY); cudaFree(c->d_WX); cudaFree(c->d_TW); cudaFree(c->d_TWK);
     cudaFree(c->d_sc); cudaFreeHost(c->h_sc);
     if (c->d_force) cudaFree(c->d_force);
     for (int s = 0; s < NSB_FORCE_RING; ++s) {
@@ -993,11 +1008,11 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
          * room for 8- or 4-column batches only; such CTAs are alone on their SM (256 threads) */
         int bdiv = half ? 2 : 1;
         const size_t smem_cap = 227 * 1024;
-        while (g.BC / bdiv > 4 && 2 * (tileB / bdiv) + 64 + 128 + twtab / bdiv > smem_cap) bdiv *= 2;
+        while (g.BC / bdiv > 4 && 2 * (tileB / bdiv) + 64 + 128 + 2 * twtab / bdiv > smem_cap) bdiv *= 2;
         const bool narrow = bdiv > 1;
-        const bool two_ctas = half && bdiv == 2 && 2 * (2 * (tileB / 2) + 64 + 128 + twtab / 2 + 1024) <= smem_cap;
+        const bool two_ctas = half && bdiv == 2 && 2 * (2 * (tileB / 2) + 64 + 128 + 2 * twtab / 2 + 1024) <= smem_cap;
         half = narrow;
-        const bool use_tma = c->ch_btma && 2 * (tileB / bdiv) + 64 + 128 + twtab / bdiv <= smem_cap && 2 * g.BC <= 256;
+        const bool use_tma = c->ch_btma && 2 * (tileB / bdiv) + 64 + 128 + 2 * twtab / bdiv <= smem_cap && 2 * g.BC <= 256;
         if (!use_tma && tileB > smem_cap)
             return fail("the chain's B tile (%zu bytes) needs the TMA-fed kernel at this size (NSB_CHAIN_BTMA=1)", tileB);
         NsbGeom gB = g;
@@ -1006,6 +1021,9 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
             gB.BC = g.BC / bdiv;
             aB.nbatch = (g.X2h + 1 + gB.BC - 1) / gB.BC;
         }
+        aB.fd_perg = nsb_fastdiv_make((unsigned)((aB.nd + aB.nm) * gB.BC));
+        aB.fd_nb = nsb_fastdiv_make((unsigned)aB.nbatch);
+        aB.fd_nb2 = nsb_fastdiv_make((unsigned)(2 * aB.nbatch));
         nsb_tmap *tm = half ? &c->tmT8 : &c->tmT;
         if (use_tma) {
             int *tm_ok = half ? &c->tmT8_ok : &c->tmT_ok;
@@ -1017,7 +1035,7 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
             }
         }
         const size_t tB = tileB / bdiv;
-        const size_t smemB = 2 * tB + 64 + 128 + twtab / bdiv;
+        const size_t smemB = 2 * tB + 64 + 128 + 2 * twtab / bdiv;
         if (split) {
             CK(cudaEventRecord(c->ch_ev[0], c->stream)); /* everything before the chain (alpha, barrier) */
             CK(cudaStreamWaitEvent(c->stream2, c->ch_ev[0], 0));
@@ -1063,7 +1081,18 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
             if (split) CK(cudaEventRecord(c->ch_ev[1 + (pc & 1)], st));
             const dim3 gridG((NP + Wg - 1) / Wg, a.nslab);
             prof_pre(c, PK_GAMMA);
-            if (c->ch_gpersist && !split) {
+            if (c->ch_g2) {
+                /* persistent, 8 warps per SM in both variants (parking in tensor memory) */
+                if (want_umax) {
+                    auto k = k_chain_G2<true>;
+                    if (ensure_smem(c, k, NSB_CHG2_SMEM, true)) return -1;
+                    NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), NSB_CHG2_SMEM, st, g, a);
+                } else {
+                    auto k = k_chain_G2<false>;
+                    if (ensure_smem(c, k, NSB_CHG2_SMEM, true)) return -1;
+                    NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), NSB_CHG2_SMEM, st, g, a);
+                }
+            } else if (c->ch_gpersist && !split) {
                 if (want_umax) {
                     auto k = k_chain_Gp<true>;
                     if (ensure_smem(c, k, smemGp, true)) return -1;

@@ -55,6 +55,25 @@ __device__ __forceinline__ void nsb_backoff() { __nanosleep(64); }
 __device__ __forceinline__ void nsb_fence_system() { __threadfence_system(); }
 #endif
 
+/* n / d for CTA-uniform runtime divisors without the I2F/MUFU division sequence (10 % of the stall samples of
+ * the round-1 B kernel sat on it): m = ceil(2^32 / d), exact while n * d < 2^32. d == 1 is encoded as m == 0. */
+struct NsbFastDiv {
+    unsigned d, m;
+};
+NSB_HD inline NsbFastDiv nsb_fastdiv_make(unsigned d) {
+    NsbFastDiv f;
+    f.d = d;
+    f.m = d <= 1 ? 0u : (unsigned)((0x100000000ull + d - 1) / d);
+    return f;
+}
+#ifdef NSB_EMULATE
+static inline unsigned nsb_fastdiv(unsigned n, NsbFastDiv f) { return f.m ? (unsigned)(((unsigned long long)n * f.m) >> 32) : n; }
+static inline int nsb_log2i(int v) { return 31 - __builtin_clz((unsigned)v); }
+#else
+__device__ __forceinline__ unsigned nsb_fastdiv(unsigned n, NsbFastDiv f) { return f.m ? __umulhi(n, f.m) : n; }
+__device__ __forceinline__ int nsb_log2i(int v) { return 31 - __clz(v); }
+#endif
+
 /* correctly rounded FP64 reciprocal (MUFU.RCP64H + Newton, inlined: no division subroutine) */
 #ifdef NSB_EMULATE
 static inline double nsb_drcp(double a) { return 1.0 / a; }
@@ -223,6 +242,155 @@ __device__ __forceinline__ void nsb_tma_store_commit() { asm volatile("cp.async.
 __device__ __forceinline__ void nsb_tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+#endif
+
+
+/*
+ * Tensor memory (TMEM, 256 KB per SM: 128 lanes x 512 columns x 32 bit) used as a LANE-PRIVATE PARKING LOT:
+ * the comb kernel parks the real products / Jacobians it has to keep across a register-resident FFT-1024
+ * there (tcgen05.st / tcgen05.ld, SASS STTM / LDTM) instead of in shared memory, which frees 128-192 KB of
+ * shared memory per SM for TMA landing buffers. A warp may touch only the 32 lanes of its own quadrant
+ * (warp % 4); thread t of the warp owns lane 32 * (warp % 4) + t; columns are 32-bit, one double = 2 columns.
+ * No tensor-core instruction is involved. Under the CPU emulator TMEM is a plain per-CTA array.
+ */
+#ifdef NSB_EMULATE
+static inline unsigned nsb_tmem_alloc_all(unsigned *) { /* like the real one: contains a block barrier */
+    if (nsbemu::g.cur->warp == 0 && nsbemu::g.cur->lane == 0) memset(nsbemu::g.tmem, 0xff, sizeof(nsbemu::g.tmem));
+    nsbemu::barrier();
+    return 0u;
+}
+static inline void nsb_tmem_free_all(unsigned) {}
+static inline unsigned nsb_tmem_warp_base(unsigned base, int warp, int col) {
+    return base + (((unsigned)(32 * (warp & 3))) << 16) + (unsigned)col;
+}
+template <int N>
+static inline void nsb_tmem_stN(unsigned taddr, const double (&v)[N]) {
+    const unsigned lane = (taddr >> 16) + (unsigned)nsbemu::g.cur->lane, col = taddr & 0xffffu;
+    memcpy(&nsbemu::g.tmem[lane][col], v, 8 * N);
+}
+template <int N>
+static inline void nsb_tmem_ldN(double (&v)[N], unsigned taddr) {
+    const unsigned lane = (taddr >> 16) + (unsigned)nsbemu::g.cur->lane, col = taddr & 0xffffu;
+    memcpy(v, &nsbemu::g.tmem[lane][col], 8 * N);
+}
+static inline void nsb_tmem_st16(unsigned t, const double (&v)[16]) { nsb_tmem_stN<16>(t, v); }
+static inline void nsb_tmem_ld16(double (&v)[16], unsigned t) { nsb_tmem_ldN<16>(v, t); }
+static inline void nsb_tmem_st8(unsigned t, const double (&v)[8]) { nsb_tmem_stN<8>(t, v); }
+static inline void nsb_tmem_ld8(double (&v)[8], unsigned t) { nsb_tmem_ldN<8>(v, t); }
+static inline void nsb_tmem_wait_st() {}
+static inline void nsb_tmem_wait_ld() {}
+#else
+/* one warp allocates all 512 columns (one CTA per SM by construction), every thread gets the base address */
+__device__ __forceinline__ unsigned nsb_tmem_alloc_all(unsigned *slot_smem) {
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(nsb_smem_addr(slot_smem))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *reinterpret_cast<volatile unsigned *>(slot_smem);
+}
+/* all warps must be done with TMEM (caller synchronises the CTA first) */
+__device__ __forceinline__ void nsb_tmem_free_all(unsigned base) {
+    if ((threadIdx.x >> 5) == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base) : "memory");
+}
+__device__ __forceinline__ unsigned nsb_tmem_warp_base(unsigned base, int warp, int col) {
+    return base + (((unsigned)(32 * (warp & 3))) << 16) + (unsigned)col;
+}
+/* N doubles of this thread <-> 2N consecutive columns of its own lane, starting at column (taddr & 0xffff) */
+__device__ __forceinline__ void nsb_tmem_st8(unsigned taddr, const double (&v)[8]) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15;\n"
+        "mov.b64 {a0, a1}, %1;\n"
+        "mov.b64 {a2, a3}, %2;\n"
+        "mov.b64 {a4, a5}, %3;\n"
+        "mov.b64 {a6, a7}, %4;\n"
+        "mov.b64 {a8, a9}, %5;\n"
+        "mov.b64 {a10, a11}, %6;\n"
+        "mov.b64 {a12, a13}, %7;\n"
+        "mov.b64 {a14, a15}, %8;\n"
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15};\n"
+        "}\n" ::"r"(taddr),
+        "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "d"(v[4]), "d"(v[5]), "d"(v[6]), "d"(v[7])
+        : "memory");
+}
+__device__ __forceinline__ void nsb_tmem_ld8(double (&v)[8], unsigned taddr) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15;\n"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15}, [%8];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        "mov.b64 %0, {a0, a1};\n"
+        "mov.b64 %1, {a2, a3};\n"
+        "mov.b64 %2, {a4, a5};\n"
+        "mov.b64 %3, {a6, a7};\n"
+        "mov.b64 %4, {a8, a9};\n"
+        "mov.b64 %5, {a10, a11};\n"
+        "mov.b64 %6, {a12, a13};\n"
+        "mov.b64 %7, {a14, a15};\n"
+        "}\n"
+        : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void nsb_tmem_st16(unsigned taddr, const double (&v)[16]) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15, a16, a17, a18, a19, a20, a21, a22, a23, a24, a25, a26, a27, a28, a29, a30, a31;\n"
+        "mov.b64 {a0, a1}, %1;\n"
+        "mov.b64 {a2, a3}, %2;\n"
+        "mov.b64 {a4, a5}, %3;\n"
+        "mov.b64 {a6, a7}, %4;\n"
+        "mov.b64 {a8, a9}, %5;\n"
+        "mov.b64 {a10, a11}, %6;\n"
+        "mov.b64 {a12, a13}, %7;\n"
+        "mov.b64 {a14, a15}, %8;\n"
+        "mov.b64 {a16, a17}, %9;\n"
+        "mov.b64 {a18, a19}, %10;\n"
+        "mov.b64 {a20, a21}, %11;\n"
+        "mov.b64 {a22, a23}, %12;\n"
+        "mov.b64 {a24, a25}, %13;\n"
+        "mov.b64 {a26, a27}, %14;\n"
+        "mov.b64 {a28, a29}, %15;\n"
+        "mov.b64 {a30, a31}, %16;\n"
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15, a16, a17, a18, a19, a20, a21, a22, a23, a24, a25, a26, a27, a28, a29, a30, a31};\n"
+        "}\n" ::"r"(taddr),
+        "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "d"(v[4]), "d"(v[5]), "d"(v[6]), "d"(v[7]), "d"(v[8]), "d"(v[9]), "d"(v[10]), "d"(v[11]), "d"(v[12]), "d"(v[13]), "d"(v[14]), "d"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void nsb_tmem_ld16(double (&v)[16], unsigned taddr) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15, a16, a17, a18, a19, a20, a21, a22, a23, a24, a25, a26, a27, a28, a29, a30, a31;\n"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15, a16, a17, a18, a19, a20, a21, a22, a23, a24, a25, a26, a27, a28, a29, a30, a31}, [%16];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        "mov.b64 %0, {a0, a1};\n"
+        "mov.b64 %1, {a2, a3};\n"
+        "mov.b64 %2, {a4, a5};\n"
+        "mov.b64 %3, {a6, a7};\n"
+        "mov.b64 %4, {a8, a9};\n"
+        "mov.b64 %5, {a10, a11};\n"
+        "mov.b64 %6, {a12, a13};\n"
+        "mov.b64 %7, {a14, a15};\n"
+        "mov.b64 %8, {a16, a17};\n"
+        "mov.b64 %9, {a18, a19};\n"
+        "mov.b64 %10, {a20, a21};\n"
+        "mov.b64 %11, {a22, a23};\n"
+        "mov.b64 %12, {a24, a25};\n"
+        "mov.b64 %13, {a26, a27};\n"
+        "mov.b64 %14, {a28, a29};\n"
+        "mov.b64 %15, {a30, a31};\n"
+        "}\n"
+        : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]), "=d"(v[8]), "=d"(v[9]), "=d"(v[10]), "=d"(v[11]), "=d"(v[12]), "=d"(v[13]), "=d"(v[14]), "=d"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void nsb_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void nsb_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 #endif
 
 #endif

@@ -63,6 +63,7 @@ struct State {
     std::vector<int> warp_live, warp_arrived;
     std::vector<unsigned> warp_gen;
     std::vector<double> warp_buf;
+    uint32_t tmem[128][512]; /* tensor memory of the current CTA (nsb_platform.h: nsb_tmem_*) */
 };
 extern State g;
 void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> body);
