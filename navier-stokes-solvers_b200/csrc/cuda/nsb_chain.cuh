@@ -385,14 +385,19 @@ __device__ __forceinline__ void chain_seg_range(const NsbGeom &g, int nd, int se
  * at tile[(fi*nseg + seg)*16 + row][pos]. Columns outside the retained set come back as
  * zeros or as neighbouring retained columns; step 1 masks them by range. Completion on `bar`.
  */
+#ifndef NSB_B_TW_TMA
+#define NSB_B_TW_TMA 1
+#endif
+template <bool TW_TMA>
 __device__ __forceinline__ void chain_B_issue(const NsbGeom &g, const ChainArgs &a, const nsb_tmap *tmT, cd *tile,
                                               cd *twtab, nsb_mbar_t *bar, int slab, int pp, int kb) {
     const int nseg = a.nd + a.nm;
     if (threadIdx.x == 0) {
         nsb_fence_proxy_async();
-        nsb_mbar_expect_tx(bar, (unsigned)(2 * nseg) * (unsigned)(a.R * g.BC * 16) + (unsigned)(g.BC * g.X1 * 16));
+        const unsigned twb = TW_TMA ? (unsigned)(g.BC * NSB_TWK_PITCH(g.X1) * 16) : 0u;
+        nsb_mbar_expect_tx(bar, (unsigned)(2 * nseg) * (unsigned)(a.R * g.BC * 16) + twb);
         /* the x twiddles of this k2 batch: one contiguous block of the batch-ordered table */
-        nsb_bulk_g2s(twtab, g.TWK + (size_t)kb * g.X1, (unsigned)(g.BC * g.X1 * 16), bar);
+        if (TW_TMA) nsb_bulk_g2s(twtab, g.TWK + (size_t)kb * NSB_TWK_PITCH(g.X1), twb, bar);
     }
     __syncthreads();
     if ((int)threadIdx.x < 2 * nseg) {
@@ -449,10 +454,10 @@ __device__ __forceinline__ void chain_gather_mo(cd (&x)[X1], const cd *tile, int
     }
 }
 
-/* twtab (nullable): shared-memory copy of the x twiddles of this batch, twtab[cc*X1 + x1].
- * (This cc-major layout is an 8-way bank conflict for the 16 lanes of a row, 60 % of the kernel's
- * shared-memory wavefronts in the ncu capture; the conflict-free x1-major layout was measured
- * SLOWER, 4.15 vs 3.56 ms at 16384^2 and 0.35 vs 0.31 ms at 4096^2, so it stays. Unexplained.) */
+/* twtab (nullable): shared-memory copy of the x twiddles of this batch, twtab[cc*(X1+1) + x1]: rows padded by one
+ * element so that the 8 lanes of a 128-bit shared-memory phase (consecutive cc, same x1) fall into 8 different
+ * 16-byte bank groups (with pitch X1 they were an 8-way conflict: 60 % of the round-1 kernel's shared-memory
+ * wavefronts and a 32-cycle pipe occupancy per twiddle load, which the twiddle multiply then waited for). */
 template <int X1, bool MO>
 __device__ __forceinline__ void chain_B_step2x(const NsbGeom &g, const ChainArgs &a, const cd *tile, int slot, int pp,
                                                int kb, const cd *twtab) {
@@ -481,7 +486,7 @@ __device__ __forceinline__ void chain_B_step2x(const NsbGeom &g, const ChainArgs
         for (int x1 = 0; x1 < X1; ++x1) {
             cd av = A[x1], bv = B[x1];
             if (X1 > 1) {
-                const cd tw = twtab ? twtab[cc * X1 + x1] : __ldg(&g.WX[(size_t)k2 * x1]);
+                const cd tw = twtab ? twtab[cc * NSB_TWK_PITCH(X1) + x1] : __ldg(&g.WX[(size_t)k2 * x1]);
                 av = cmulc(av, tw);
                 bv = cmulc(bv, tw);
             }
@@ -553,7 +558,7 @@ __device__ __forceinline__ void chain_B_step2p(const NsbGeom &g, const ChainArgs
         const bool special = (k2 == 0 || k2 == g.X2h);
 #pragma unroll
         for (int x1 = 0; x1 < X1; ++x1) {
-            cd v = cmulc(x[x1], twtab[cc * X1 + x1]);
+            cd v = cmulc(x[x1], twtab[cc * NSB_TWK_PITCH(X1) + x1]);
             if (special_batch) { /* batch-uniform: every lane shuffles */
                 const double ox = __shfl_xor_sync(0xffffffffu, v.x, 1), oy = __shfl_xor_sync(0xffffffffu, v.y, 1);
                 if (special) v = cmk(0.5 * (v.x + ox), 0.5 * (v.y - oy)); /* half 0: (Re a, Re b) */
@@ -573,7 +578,9 @@ __device__ __forceinline__ void chain_B_step2p(const NsbGeom &g, const ChainArgs
  * is off the critical path with one CTA per SM.
  * smem: 2 stages x (2*16*nseg*BC complex) + 2 mbarriers (+128 B alignment slack).
  */
-template <int NT, int MINB, bool BIG>
+/* SPLIT: step 2 with the Hermitian packing in front of the k1 DFT (chain_B_step2p: one thread transforms A + iB, another
+ * A - iB, ONE 16-point array per thread instead of two): half the registers per thread, so 512 threads fit one SM. */
+template <int NT, int MINB, bool BIG, bool SPLIT = false>
 __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a, const NSB_GRID_CONSTANT nsb_tmap tmT) {
     NSB_DYN_SMEM(cd, smem_raw);
     /* 128-byte alignment for the TMA destination. (Measured: keeping shared-memory provenance, i.e.
@@ -583,7 +590,7 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
     const size_t tile_elems = (size_t)2 * a.R * nseg * g.BC;
     nsb_mbar_t *bars = reinterpret_cast<nsb_mbar_t *>(smem + 2 * tile_elems);
     cd *twtabs = smem + 2 * tile_elems + 4; /* 2 stages x BC * X1 x twiddles (TMA bulk copies, with the tile) */
-    const size_t tw_elems = (size_t)g.BC * g.X1;
+    const size_t tw_elems = (size_t)g.BC * NSB_TWK_PITCH(g.X1);
     if (threadIdx.x == 0) {
         nsb_mbar_init(&bars[0], 1);
         nsb_mbar_init(&bars[1], 1);
@@ -602,7 +609,7 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
     if (item < nitems) {
         int slab, pp, kb;
         decode(item, &slab, &pp, &kb);
-        chain_B_issue(g, a, &tmT, smem, twtabs, &bars[0], slab, pp, kb);
+        chain_B_issue<NSB_B_TW_TMA && !BIG>(g, a, &tmT, smem, twtabs, &bars[0], slab, pp, kb);
     }
     for (int n = 0; item < nitems; ++n, item += gridDim.x) {
         const int st = n & 1;
@@ -610,15 +617,22 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
         if (next < nitems) {
             int slab, pp, kb;
             decode(next, &slab, &pp, &kb);
-            chain_B_issue(g, a, &tmT, smem + (size_t)(st ^ 1) * tile_elems, twtabs + (size_t)(st ^ 1) * tw_elems,
-                          &bars[st ^ 1], slab, pp, kb);
+            chain_B_issue<NSB_B_TW_TMA && !BIG>(g, a, &tmT, smem + (size_t)(st ^ 1) * tile_elems, twtabs + (size_t)(st ^ 1) * tw_elems,
+                               &bars[st ^ 1], slab, pp, kb);
         }
         nsb_mbar_wait(&bars[st], phase[st]);
         phase[st] ^= 1u;
         cd *tile = smem + (size_t)st * tile_elems;
-        const cd *twtab = twtabs + (size_t)st * tw_elems;
         int slab, pp, kb;
         decode(item, &slab, &pp, &kb);
+        if constexpr (BIG || !NSB_B_TW_TMA) { /* 32-point factors: the twiddles of the batch are gathered by the threads
+                              * (measured: the TMA-staged table costs this variant a factor of two) */
+            cd *tw = twtabs + (size_t)st * tw_elems;
+            for (int w = threadIdx.x; w < g.BC * g.X1; w += blockDim.x) {
+                const int cc = w / g.X1, x1 = w - cc * g.X1;
+                tw[cc * NSB_TWK_PITCH(g.X1) + x1] = (kb + cc <= g.X2h) ? __ldg(&g.WX[(size_t)(kb + cc) * x1]) : cmk(1.0, 0.0);
+            }
+        }
         switch (g.Y2) {
             case 1: chain_B2_step1<1>(g, a, tile, kb); break;
             case 2: chain_B2_step1<2>(g, a, tile, kb); break;
@@ -630,16 +644,27 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
                 break;
         }
         __syncthreads();
-        const int slot = slab % a.nslotZ;
-        switch (g.X1) {
-            case 1: chain_B_step2x<1, true>(g, a, tile, slot, pp, kb, twtab); break;
-            case 2: chain_B_step2x<2, true>(g, a, tile, slot, pp, kb, twtab); break;
-            case 4: chain_B_step2x<4, true>(g, a, tile, slot, pp, kb, twtab); break;
-            case 8: chain_B_step2x<8, true>(g, a, tile, slot, pp, kb, twtab); break;
-            case 16: chain_B_step2x<16, true>(g, a, tile, slot, pp, kb, twtab); break;
-            default:
-                if constexpr (BIG) chain_B_step2p<32>(g, a, tile, slot, pp, kb, twtab);
-                break;
+        const cd *twtab = twtabs + (size_t)st * tw_elems;
+        const int slot = slab; /* plain chain: every slab has its own Z slot (nslotZ == slabs of the device) */
+        if constexpr (SPLIT) {
+            switch (g.X1) {
+                case 2: chain_B_step2p<2>(g, a, tile, slot, pp, kb, twtab); break;
+                case 4: chain_B_step2p<4>(g, a, tile, slot, pp, kb, twtab); break;
+                case 8: chain_B_step2p<8>(g, a, tile, slot, pp, kb, twtab); break;
+                case 16: chain_B_step2p<16>(g, a, tile, slot, pp, kb, twtab); break;
+                default: break;
+            }
+        } else {
+            switch (g.X1) {
+                case 1: chain_B_step2x<1, true>(g, a, tile, slot, pp, kb, twtab); break;
+                case 2: chain_B_step2x<2, true>(g, a, tile, slot, pp, kb, twtab); break;
+                case 4: chain_B_step2x<4, true>(g, a, tile, slot, pp, kb, twtab); break;
+                case 8: chain_B_step2x<8, true>(g, a, tile, slot, pp, kb, twtab); break;
+                case 16: chain_B_step2x<16, true>(g, a, tile, slot, pp, kb, twtab); break;
+                default:
+                    if constexpr (BIG) chain_B_step2p<32>(g, a, tile, slot, pp, kb, twtab);
+                    break;
+            }
         }
         __syncthreads(); /* the tile is free for the copies of item n+2 */
     }

@@ -89,6 +89,7 @@ struct nsb_ctx {
     int tmT_ok, tmT8_ok;
     int ch_bbc;
     int ch_gpersist;
+    int ch_b512; /* B with split step 2 and twice the threads (k_chain_B_tma<512, 1, false, true>) */
     int ch_g2; /* G with TMEM parking + TMA-fed inputs (k_chain_G2) */
     int ch_pieces;          /* slab ranges of the chain run on two streams (1 = one range, one stream) */
     cudaStream_t stream2;
@@ -278,6 +279,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->ch_fthreads = env_int("NSB_CHAIN_FTHREADS", 128) == 256 ? 256 : 128; /* F with 32-point factors only */
     c->ch_pieces = env_int("NSB_CHAIN_PIECES", 0);         /* 0 = automatic */
     c->ch_g2 = env_int("NSB_CHAIN_G2", 1);
+    c->ch_b512 = env_int("NSB_CHAIN_B512", 1);
     c->ch_gpersist = env_int("NSB_CHAIN_GPERSIST", 0); /* measured: the persistent G is 6 % slower (2.93 vs 2.77 ms) */
     c->alpha_cols = env_int("NSB_ALPHA_COLS", 4) == 8 ? 8 : 4;
     c->alpha_tma = env_int("NSB_ALPHA_TMA", 1);
@@ -358,9 +360,9 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
         std::vector<cd> wx, twk;
         fill_twiddles(wx, g.nx);
         const int nk2 = ((g.X2h + 1 + 15) / 16) * 16;
-        twk.assign((size_t)nk2 * g.X1, make_double2(1.0, 0.0));
+        twk.assign((size_t)nk2 * NSB_TWK_PITCH(g.X1), make_double2(1.0, 0.0));
         for (int k2 = 0; k2 <= g.X2h; ++k2)
-            for (int x1 = 0; x1 < g.X1; ++x1) twk[(size_t)k2 * g.X1 + x1] = wx[((size_t)k2 * x1) % g.nx];
+            for (int x1 = 0; x1 < g.X1; ++x1) twk[(size_t)k2 * NSB_TWK_PITCH(g.X1) + x1] = wx[((size_t)k2 * x1) % g.nx];
         CK(cudaMalloc((void **)&c->d_TWK, twk.size() * sizeof(cd)));
         CK(cudaMemcpy(c->d_TWK, twk.data(), twk.size() * sizeof(cd), cudaMemcpyHostToDevice));
         g.TWK = c->d_TWK;
@@ -962,7 +964,7 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
     const int NP = a.NQ / 2;
     const int W = (c->chain_mode == 2 && c->ch_ctas == 2) ? (want_umax ? 3 : 4) : (want_umax ? 6 : 8);
     const size_t tileB = (size_t)2 * R * (a.nd + a.nm) * g.BC * sizeof(cd);
-    const size_t twtab = (size_t)g.BC * g.X1 * sizeof(cd);
+    const size_t twtab = (size_t)g.BC * NSB_TWK_PITCH(g.X1) * sizeof(cd);
     /* F keeps one tile per CTA; with 32-point factors a 16-column tile (180 KB) would leave one CTA per
      * SM, so its batches narrow to 8 columns there (16384^2 and below: unchanged, 45 KB) */
     int bcF = g.BC;
@@ -990,7 +992,8 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
          * 16 ranges 8.93 / 8.83 / 8.70 / 9.01 / 9.23 ms per step; 4 devices (256 slabs each) 1 / 4 / 8 ranges
          * 15.55 / 15.48 / 15.18 ms */
         const int auto_pieces =
-            total_slabs >= 512 ? 16 : ((c->mg_world > 1 && !big && total_slabs >= 128) ? total_slabs / 32 : 1);
+            total_slabs >= 512 ? ((c->ch_b512 && g.X1 >= 2 && !big) ? 4 : 16)
+                               : ((c->mg_world > 1 && !big && total_slabs >= 128) ? total_slabs / 32 : 1);
         int pieces = c->prof_on ? 1 : (c->ch_pieces > 0 ? c->ch_pieces : auto_pieces);
         if (pieces > total_slabs) pieces = total_slabs;
         const bool split = pieces > 1;
@@ -1003,7 +1006,10 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
         const size_t smemGp = NSB_CH_TW_BYTES + (size_t)Wg * (want_umax ? NSB_CHG_WARP_BYTES(1) : NSB_CHG_WARP_BYTES(0));
         /* measured: 8-column batches win while the tile is small (4096^2: 0.31 vs 0.40 ms), 16-column
          * batches with one 256-thread CTA per SM win at 16384^2 (3.56 vs 5.58 ms) when B runs alone */
-        bool half = g.BC == 16 && (split || c->ch_bbc == 8 || (c->ch_bbc < 0 && tileB <= 48 * 1024));
+        /* round 2: with the split step 2 (512 threads, 128 registers) the 16-column batch wins at 16384^2 also
+         * inside slab ranges (43.0 ms per step in 4 ranges against 45.9 with 8-column batches in 16) */
+        const bool b512 = c->ch_b512 && g.X1 >= 2 && !big;
+        bool half = g.BC == 16 && (c->ch_bbc == 8 || (c->ch_bbc < 0 && ((split && !b512) || tileB <= 48 * 1024)));
         /* two tile stages must fit one SM: 32-point factors (32 rows x up to 22 segments per column) leave
          * room for 8- or 4-column batches only; such CTAs are alone on their SM (256 threads) */
         int bdiv = half ? 2 : 1;
@@ -1053,6 +1059,14 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
                     auto k = k_chain_B_tma<256, 1, true>;
                     if (ensure_smem(c, k, smemB, true)) return -1;
                     NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), smemB, st, gB, aB, *tm);
+                } else if (c->ch_b512 && g.X1 >= 2 && !narrow) {
+                    auto k = k_chain_B_tma<512, 1, false, true>;
+                    if (ensure_smem(c, k, smemB, true)) return -1;
+                    NSB_LAUNCH(k, dim3(c->sm_count), dim3(512), smemB, st, gB, aB, *tm);
+                } else if (c->ch_b512 && g.X1 >= 2 && two_ctas) {
+                    auto k = k_chain_B_tma<256, 2, false, true>;
+                    if (ensure_smem(c, k, smemB, true)) return -1;
+                    NSB_LAUNCH(k, dim3(2 * c->sm_count), dim3(256), smemB, st, gB, aB, *tm);
                 } else if (two_ctas) {
                     auto k = k_chain_B_tma<128, 2, false>;
                     if (ensure_smem(c, k, smemB, true)) return -1;

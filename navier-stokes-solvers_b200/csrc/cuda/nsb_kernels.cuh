@@ -32,6 +32,7 @@
 #include "nsb_fft1024.cuh"
 
 #define NSB_MAXP 8 /* devices of one NVSwitch domain */
+#define NSB_TWK_PITCH(X1) ((X1) + ((X1) < 32 ? 1 : 0)) /* row pitch (complex elements) of the batch-ordered x twiddle table */
 
 struct NsbGeom {
     int nx, ny, nkx;
@@ -45,8 +46,8 @@ struct NsbGeom {
     const double *kyK; /* ky permuted for the fast column kernel: kyK[j2*Y1 + j1] = ky[j1*Y2 + j2] */
     const cd *WY, *WX; /* exp(-2 pi i m/ny), exp(-2 pi i m/nx) */
     const cd *TWY, *TWX; /* warp FFT-1024 twiddles exp(-2 pi i t r/1024) at [r*32 + t] (ny, nx >= 1024 only) */
-    const cd *TWK;       /* x twiddles of the chain's B kernel in batch order: TWK[k2*X1 + x1] = WX[k2*x1], k2 <= X2h
-                          * (padded with 1 to a multiple of 16 k2): one contiguous BC*X1 block per k2 batch */
+    const cd *TWK;       /* x twiddles of the chain's B kernel in batch order: TWK[k2*(X1+1) + x1] = WX[k2*x1], k2 <= X2h
+                          * (padded with 1 to a multiple of 16 k2): one contiguous block per k2 batch */
     double norm;       /* 1/(nx*ny) */
 };
 

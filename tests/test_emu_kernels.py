@@ -113,8 +113,8 @@ def test_emu_chain_ring_reuse(nsb, emu_lib, oracles, monkeypatch):
 
 
 def test_emu_chain_matches_plain_kernels(nsb, emu_lib, monkeypatch):
-    """Plain and persistent chain run the same item code: bit-identical. Against the separate
-    beta/gamma kernels only the Hermitian packing differs (psi_x + i omega_y instead of
+    """Plain and persistent chain against each other and against the separate
+    beta/gamma kernels: only the Hermitian packing differs (psi_x + i omega_y instead of
     psi_x + i psi_y), i.e. rounding-level differences."""
     import numpy as np
     rng = np.random.default_rng(5)
@@ -131,7 +131,8 @@ def test_emu_chain_matches_plain_kernels(nsb, emu_lib, monkeypatch):
         c.step(0.0)
         out[mode] = (c.download(nsb.OMEGA_HAT), c.state()[0])
         c.close()
-    assert np.array_equal(out[1][0], out[2][0]) and out[1][1] == out[2][1]
+    # plain (packing in front of the k1 DFT since round 2) vs persistent (behind it): rounding level
+    assert pc.rel(out[1][0], out[2][0]) < 1e-14 and abs(out[1][1] - out[2][1]) <= 1e-15 * out[2][1]
     assert pc.rel(out[1][0], out[0][0]) < 1e-14
     assert abs(out[1][1] - out[0][1]) <= 1e-15 * out[0][1]
 

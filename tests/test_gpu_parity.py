@@ -241,8 +241,8 @@ def test_step_chain_modes(nsb, cuda_lib, oracles, monkeypatch, mode, n, steps):
 
 
 def test_chain_persistent_equals_plain_8192(nsb, cuda_lib, monkeypatch):
-    """Ring reuse and counter waits at scale: the persistent kernel must reproduce the plain
-    kernels bit for bit (same item code, different schedule), also with tiny rings."""
+    """Ring reuse and counter waits at scale: the persistent kernel must reproduce itself bit for bit with
+    tiny rings (same item code, different schedule) and the plain kernels to rounding level."""
     n = 8192
     rng = np.random.default_rng(11)
     w = np.zeros((n, n // 2 + 1), dtype=np.complex128)
@@ -267,9 +267,12 @@ def test_chain_persistent_equals_plain_8192(nsb, cuda_lib, monkeypatch):
             c.step(0.0)
         out.append((c.download(nsb.OMEGA_HAT), c.state()[0]))
         c.close()
-    for o in out[1:]:
-        assert np.array_equal(o[0], out[0][0])
-        assert o[1] == out[0][1]
+    # the two persistent runs execute the same item code on different ring geometries: bit-identical
+    assert np.array_equal(out[2][0], out[1][0]) and out[2][1] == out[1][1]
+    # the plain chain packs the two real fields BEFORE the k1 DFT in its B kernel (round 2: one 16-point array
+    # per thread, 512 threads per SM), the persistent kernel after it: same mathematics, rounding-level differences
+    assert pc.rel(out[1][0], out[0][0]) < 1e-13
+    assert abs(out[1][1] - out[0][1]) <= 1e-12 * out[0][1]
 
 
 def _turbulence_block(n, seed, kk=64, amp=0.02):
