@@ -197,6 +197,18 @@ int nsb_mgpu_group_step(nsb_ctx **ctxs, int n, double dt);
 int nsb_mgpu_group_gather(nsb_ctx **ctxs, int n);
 int nsb_mgpu_group_scatter(nsb_ctx **ctxs, int n);
 
+/* Turbulence statistics of a velocity field (/root/reference/src/analysis/statistics.c) on the device: the raw sums
+ *   raw = { sum u, sum v, sum u'^2, sum u'^3, sum u'^4, sum v'^2, sum v'^3, sum v'^4,
+ *           sum (du'/dx)^2 (centred, periodic), sum (Sxx^2 + Syy^2 + 2 Sxy^2) }
+ * and the unnormalised two-point sums corr_x_raw[s] = sum u'(x) u'(x + s dx), s < sep_x (same along y); the
+ * caller turns them into moments, correlation functions and length scales (csrc/host/analysis.c).
+ * nsb_velocity_statistics works on the context's device-resident U, V (no transfer);
+ * nsb_velocity_statistics_host takes host arrays of ANY size nx x ny (uploads them). Synchronous. */
+int nsb_velocity_statistics(nsb_ctx *c, double dx, double dy, int sep_x, int sep_y, double raw[10],
+                            double *corr_x_raw, double *corr_y_raw);
+int nsb_velocity_statistics_host(int device, const double *u, const double *v, int nx, int ny, double dx, double dy,
+                                 int sep_x, int sep_y, double raw[10], double *corr_x_raw, double *corr_y_raw);
+
 /* Order-independent, exactly combinable fingerprint of the RK state omega_hat over the retained
  * columns this device owns ([col0, col1), all ky rows): out[0] = XOR, out[1] = wrapping 64-bit sum of
  * the IEEE-754 bit patterns of every real and imaginary part. XOR / add the results of all ranks of a

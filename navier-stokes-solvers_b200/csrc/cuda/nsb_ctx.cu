@@ -5,6 +5,7 @@
  */
 #include "nsb_kernels.cuh"
 #include "nsb_chain.cuh"
+#include "nsb_stats.cuh"
 #include "../../../include/nsb.h"
 
 #include <cmath>
@@ -2188,4 +2189,96 @@ extern "C" int nsb_energy_spectrum(nsb_ctx *c, int nbins, double *ek_sum, int *c
     cudaFree(d_ek);
     if (e != cudaSuccess) return fail("nsb_energy_spectrum: %s", cudaGetErrorString(e));
     return 0;
+}
+
+/* ---------------------------------------------------- turbulence statistics */
+
+static int stats_on_device(const double *du, const double *dv, int nx, int ny, double dx, double dy, int sep_x,
+                           int sep_y, double raw[10], double *corr_x_raw, double *corr_y_raw, cudaStream_t st,
+                           long long *launches) {
+    const size_t n = (size_t)nx * ny;
+    const size_t nscr = 10 + (size_t)sep_x + (size_t)sep_y;
+    double *d_scr = nullptr;
+    CK(cudaMalloc((void **)&d_scr, nscr * sizeof(double)));
+    cudaError_t e = cudaMemsetAsync(d_scr, 0, nscr * sizeof(double), st);
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    std::vector<double> h(nscr, 0.0);
+    if (e == cudaSuccess) {
+        auto k = k_stats_sums;
+        NSB_LAUNCH(k, dim3((unsigned)blocks), dim3(256), 256 * sizeof(double), st, du, dv, n, d_scr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), d_scr, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    const double inv_total = 1.0 / (double)n;
+    const double mean_u = h[0] * inv_total, mean_v = h[1] * inv_total; /* statistics.c:203-204 */
+    if (e == cudaSuccess) {
+        auto k = k_stats_moments;
+        NSB_LAUNCH(k, dim3((unsigned)blocks), dim3(256), 256 * sizeof(double), st, du, dv, nx, ny, mean_u, mean_v, dx, dy,
+                   d_scr + 2);
+        e = cudaGetLastError();
+    }
+    size_t cblocks = blocks > 148 * 2 ? 148 * 2 : blocks;
+    if (e == cudaSuccess && sep_x > 0) {
+        auto k = k_stats_corr;
+        NSB_LAUNCH(k, dim3((unsigned)cblocks, (unsigned)sep_x), dim3(256), 256 * sizeof(double), st, du, nx, ny, mean_u, 0,
+                   d_scr + 10);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && sep_y > 0) {
+        auto k = k_stats_corr;
+        NSB_LAUNCH(k, dim3((unsigned)cblocks, (unsigned)sep_y), dim3(256), 256 * sizeof(double), st, du, nx, ny, mean_u, 1,
+                   d_scr + 10 + sep_x);
+        e = cudaGetLastError();
+    }
+    if (launches) *launches += 2 + (sep_x > 0) + (sep_y > 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h.data() + 2, d_scr + 2, (nscr - 2) * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_scr);
+    if (e != cudaSuccess) return fail("turbulence statistics: %s", cudaGetErrorString(e));
+    for (int k = 0; k < 10; ++k) raw[k] = h[k];
+    for (int s = 0; s < sep_x; ++s) corr_x_raw[s] = h[10 + s];
+    for (int s = 0; s < sep_y; ++s) corr_y_raw[s] = h[10 + sep_x + s];
+    return 0;
+}
+
+extern "C" int nsb_velocity_statistics(nsb_ctx *c, double dx, double dy, int sep_x, int sep_y, double raw[10],
+                                       double *corr_x_raw, double *corr_y_raw) {
+    if (!c || !raw) return fail("nsb_velocity_statistics: null argument");
+    if (sep_x < 0 || sep_y < 0 || sep_x > c->g.nx || sep_y > c->g.ny || (sep_x > 0 && !corr_x_raw) || (sep_y > 0 && !corr_y_raw))
+        return fail("nsb_velocity_statistics: bad separations");
+    CK(cudaSetDevice(c->device));
+    void *u, *v;
+    if (get_field(c, NSB_U, &u) || get_field(c, NSB_V, &v)) return -1;
+    return stats_on_device((const double *)u, (const double *)v, c->g.nx, c->g.ny, dx, dy, sep_x, sep_y, raw, corr_x_raw,
+                           corr_y_raw, c->stream, &c->launches);
+}
+
+extern "C" int nsb_velocity_statistics_host(int device, const double *u, const double *v, int nx, int ny, double dx,
+                                            double dy, int sep_x, int sep_y, double raw[10], double *corr_x_raw,
+                                            double *corr_y_raw) {
+    if (!u || !v || !raw || nx <= 0 || ny <= 0) return fail("nsb_velocity_statistics_host: bad argument");
+    if (sep_x < 0 || sep_y < 0 || sep_x > nx || sep_y > ny || (sep_x > 0 && !corr_x_raw) || (sep_y > 0 && !corr_y_raw))
+        return fail("nsb_velocity_statistics_host: bad separations");
+#ifndef NSB_EMULATE
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail("no CUDA device visible: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("device %d out of range (%d visible)", device, ndev);
+#endif
+    CK(cudaSetDevice(device));
+    const size_t bytes = (size_t)nx * ny * sizeof(double);
+    double *du = nullptr, *dv = nullptr;
+    CK(cudaMalloc((void **)&du, bytes));
+    if (cudaMalloc((void **)&dv, bytes) != cudaSuccess) { cudaFree(du); return fail("out of device memory"); }
+    int rc = -1;
+    if (cudaMemcpy(du, u, bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpy(dv, v, bytes, cudaMemcpyHostToDevice) == cudaSuccess)
+        rc = stats_on_device(du, dv, nx, ny, dx, dy, sep_x, sep_y, raw, corr_x_raw, corr_y_raw, (cudaStream_t)0, nullptr);
+    else
+        fail("nsb_velocity_statistics_host: upload failed");
+    cudaFree(du);
+    cudaFree(dv);
+    return rc;
 }

@@ -39,6 +39,8 @@ static void set_error(const char *fmt, ...) {
 }
 
 const char *ns_spectral_last_error(void) { return g_error; }
+/* for the other host sources of this library (analysis.c) */
+void ns_spectral_set_error_text(const char *text) { set_error("%s", text ? text : ""); }
 
 static Backend *backend_of(const NSSpectralData *d) { return d ? (Backend *)d->backend : NULL; }
 

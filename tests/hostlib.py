@@ -52,6 +52,9 @@ SPECTRAL_SYMBOLS = [
     "ns_spectral_output_solution_strided", "ns_spectral_energy_spectrum", "ns_spectral_save_state",
     "ns_spectral_load_state",
 ]
+ANALYSIS_SYMBOLS = ["ns_stats_compute_velocity_statistics", "ns_spectral_turbulence_statistics",
+                    "ns_vtk_write_spectral_legacy", "ns_vtk_write_spectral_xml", "ns_vtk_update_pvd",
+                    "ns_spectral_write_vtk_strided"]
 FORCING_SYMBOLS = ["ns_forcing_config_default", "ns_forcing_state_init", "ns_forcing_state_free",
                    "ns_forcing_generate", "ns_forcing_box_extent", "ns_forcing_active_indices",
                    "ns_forcing_generate_box"]
@@ -69,7 +72,8 @@ NSB_SYMBOLS = [
     "nsb_launch_count",
     "nsb_mgpu_setup", "nsb_mgpu_partition", "nsb_mgpu_export", "nsb_mgpu_import", "nsb_mgpu_link_local",
     "nsb_mgpu_group_step", "nsb_mgpu_group_gather", "nsb_mgpu_group_scatter", "nsb_spectral_stats",
-    "nsb_energy_spectrum", "nsb_state_checksum", "nsb_phys_absmax", "nsb_phys_scale", "nsb_set_physics",
+    "nsb_energy_spectrum", "nsb_state_checksum", "nsb_phys_absmax", "nsb_phys_scale", "nsb_set_physics", "nsb_velocity_statistics",
+    "nsb_velocity_statistics_host",
 ]
 
 
