@@ -152,6 +152,11 @@ int nsb_phys_scale(nsb_ctx *c, int field_phys, double s);
 /* device-side scalars: last dt, time, number of steps taken. Synchronous. */
 int nsb_get_state(nsb_ctx *c, double *dt, double *t, int *steps);
 int nsb_set_time(nsb_ctx *c, double t);
+/* 1 if a device-side CFL evaluation (nsb_rk4_step with dt <= 0, nsb_cfl_timestep) has seen a NaN or Inf in
+ * max |u|^2 since OMEGA_HAT was last uploaded -- the field has blown up; *step_out = the step counter at that
+ * moment (-1 if finite). 0 if finite, < 0 on error. The reference silently continues with dt = MAX_DT
+ * (spectral_time_integration.c:14-20 never sees a NaN); SURVEY section 5 asks for the flag. Synchronous. */
+int nsb_check_finite(nsb_ctx *c, int *step_out);
 /* the last n (<= 256) step sizes, oldest first */
 int nsb_get_dt_history(nsb_ctx *c, int n, double *out);
 

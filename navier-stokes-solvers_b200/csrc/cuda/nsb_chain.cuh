@@ -216,7 +216,7 @@ __device__ __forceinline__ double chain_G_pair(const cd *z1base, const cd *z2bas
             const double J = __dsub_rn(PK[comb * 1024 + m * 32 + lane], __dmul_rn(x[m].x, x[m].y));
             if (UMAX) { /* spectral_time_integration.c:16 : |u|^2 = psi_y^2 + psi_x^2 */
                 const double px = PX[m * 32 + lane];
-                umax = fmax(umax, __dadd_rn(__dmul_rn(x[m].x, x[m].x), __dmul_rn(px, px)));
+                umax = nsb_max_sticky(umax, __dadd_rn(__dmul_rn(x[m].x, x[m].x), __dmul_rn(px, px)));
             }
             if (comb == 0) PK[m * 32 + lane] = J;
             else x[m] = cmk(PK[m * 32 + lane], J);
@@ -246,7 +246,7 @@ __device__ __forceinline__ void chain_G_item(const ChainArgs &a, unsigned char *
     double umax = chain_G_pair<UMAX>(z1, z2, po, ub + (size_t)warp * NSB_CHG_WARP_BYTES(UMAX), TW, lane);
     if (UMAX) {
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, off));
+        for (int off = 16; off > 0; off >>= 1) umax = nsb_max_sticky(umax, __shfl_xor_sync(0xffffffffu, umax, off));
         if (lane == 0) atomicMax(a.umax_bits, (unsigned long long)__double_as_longlong(umax));
     }
 }
@@ -717,11 +717,11 @@ __global__ void __launch_bounds__(256, 1) k_chain_Gp(NsbGeom g, ChainArgs a) {
             zn = a.Z + ((size_t)((s2 % a.nslotZ) * 2 + 0) * a.NQ + 2 * p2) * 1024;
         }
         const double u = chain_G_pair<UMAX>(z1, z2, po, wb, TW, lane, zn);
-        umax = fmax(umax, u);
+        umax = nsb_max_sticky(umax, u);
     }
     if (UMAX) {
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, off));
+        for (int off = 16; off > 0; off >>= 1) umax = nsb_max_sticky(umax, __shfl_xor_sync(0xffffffffu, umax, off));
         if (lane == 0) atomicMax(a.umax_bits, (unsigned long long)__double_as_longlong(umax));
     }
 }
@@ -821,7 +821,7 @@ __global__ void __launch_bounds__(256, 1) k_chain_G2(NsbGeom g, ChainArgs a) {
                     nsb_tmem_ld8(t, tcol + 128 + 16 * h);
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        umax = fmax(umax, __dadd_rn(__dmul_rn(x[8 * h + i].x, x[8 * h + i].x), __dmul_rn(t[i], t[i])));
+                        umax = nsb_max_sticky(umax, __dadd_rn(__dmul_rn(x[8 * h + i].x, x[8 * h + i].x), __dmul_rn(t[i], t[i])));
                 }
                 if (comb == 0) {
                     nsb_tmem_st8(tcol + 16 * h, j);
@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(256, 1) k_chain_G2(NsbGeom g, ChainArgs a) {
     }
     if (UMAX) {
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, off));
+        for (int off = 16; off > 0; off >>= 1) umax = nsb_max_sticky(umax, __shfl_xor_sync(0xffffffffu, umax, off));
         if (lane == 0) atomicMax(a.umax_bits, (unsigned long long)__double_as_longlong(umax));
     }
     __syncthreads(); /* every warp is done with tensor memory */

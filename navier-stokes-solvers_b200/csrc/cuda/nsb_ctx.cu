@@ -8,6 +8,18 @@
 #include "nsb_stats.cuh"
 #include "../../../include/nsb.h"
 
+#ifndef NSB_EMULATE
+#include <nvtx3/nvToolsExt.h> /* header-only NVTX 3: ranges show up under nsys / ncu --nvtx, no link dependency */
+struct NsbRange {
+    explicit NsbRange(const char *name) { nvtxRangePushA(name); }
+    ~NsbRange() { nvtxRangePop(); }
+};
+#else
+struct NsbRange {
+    explicit NsbRange(const char *) {}
+};
+#endif
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -110,6 +122,14 @@ struct nsb_ctx {
     cudaEvent_t mg_ev;
     int sm_count;
     long long launches;
+    /* CUDA-graph replay of the device-dt step on launch-bound (small) grids */
+    int graph_mode;            /* NSB_GRAPH: -1 automatic (grids up to 4096^2), 0 off, 1 always */
+    int graph_warm;            /* consecutive plain steps taken with the current key */
+    long long graph_launches;  /* kernels inside the captured step */
+    unsigned char graph_key[192];
+#ifndef NSB_EMULATE
+    cudaGraphExec_t graph_exec;
+#endif
     std::map<const void *, size_t> *smem_set; /* kernel -> dynamic shared memory size its attribute allows */
     cudaEvent_t ev0, ev1;
     /* optional per-kernel CUDA-event timing (nsb_profile_begin/_end) */
@@ -220,6 +240,13 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->device = p->device;
     c->smem_set = new std::map<const void *, size_t>();
     c->launches = 0;
+    c->graph_mode = getenv("NSB_GRAPH") ? atoi(getenv("NSB_GRAPH")) : -1;
+    c->graph_warm = 0;
+    c->graph_launches = 0;
+    memset(c->graph_key, 0, sizeof(c->graph_key));
+#ifndef NSB_EMULATE
+    c->graph_exec = nullptr;
+#endif
     c->prof_on = 0;
     c->prof_ev = new std::vector<cudaEvent_t>();
     c->prof_kind = new std::vector<int>();
@@ -419,6 +446,9 @@ extern "C" void nsb_ctx_destroy(nsb_ctx *c) {
         cudaEventDestroy(c->force_ev[s]);
     }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+#ifndef NSB_EMULATE
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+#endif
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->stream2);
     for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ch_ev[k]);
@@ -569,7 +599,10 @@ extern "C" int nsb_upload(nsb_ctx *c, int field, const void *host) {
     const size_t bytes = field_is_phys(field) ? c->N * sizeof(double) : c->M * sizeof(cd);
     CK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (field == NSB_OMEGA_HAT) return scan_masked(c);
+    if (field == NSB_OMEGA_HAT) {
+        CK(cudaMemsetAsync(&c->d_sc->nonfinite, 0, sizeof(unsigned), c->stream)); /* a new state: new verdict */
+        return scan_masked(c);
+    }
     return 0;
 }
 
@@ -1477,6 +1510,13 @@ static void fill_rk(nsb_ctx *c, NsbRk &rk, int stage) {
 }
 
 static int fast_phase(nsb_ctx *c, int ph, double dt) {
+    static const char *const names[NSB_FAST_PHASES] = {
+        "nsb stage 1: spectral ops + inverse y FFT (k_alpha1024)", "nsb stage 1: chain B/G/F (x transforms, Jacobian, max|u|)",
+        "nsb stage 1: CFL dt, forward y FFT + RK + stage 2 inverse", "nsb stage 2: chain B/G/F",
+        "nsb stage 2: forward y FFT + RK + stage 3 inverse", "nsb stage 3: chain B/G/F",
+        "nsb stage 3: forward y FFT + RK + stage 4 inverse", "nsb stage 4: chain B/G/F",
+        "nsb stage 4: forward y FFT + RK final combine"};
+    NsbRange range(names[ph]);
     const bool device_dt = !(dt > 0.0);
     CK(cudaSetDevice(c->device));
     if (ph == 0) {
@@ -1530,9 +1570,8 @@ static int peer_barrier_ipc(nsb_ctx *c) {
 
 static bool fast_chain_ok(const nsb_ctx *c) { return alpha_fast_ok(c) && c->chain_mode == 1; }
 
-extern "C" int nsb_rk4_step(nsb_ctx *c, double dt) {
-    if (!c) return fail("null context");
-    CK(cudaSetDevice(c->device));
+static int rk4_step_launch(nsb_ctx *c, double dt) {
+    NsbRange range("nsb_rk4_step");
     if (fast_chain_ok(c)) {
         if (c->mg_world > 1 && !c->mg_ipc)
             return fail("this context is part of a single-process device group: use nsb_mgpu_group_step");
@@ -1661,6 +1700,83 @@ extern "C" int nsb_rk4_step(nsb_ctx *c, double dt) {
     return 0;
 }
 
+/*
+ * ns_spectral_advance_rk4 with the CFL step computed on the device is a fixed sequence of 11-55 kernel launches
+ * whose arguments only change when the caller changes the configuration; on small grids (BASELINE config 2:
+ * 1024^2, 0.3 ms per step) the launches themselves are a visible share of the step. The sequence is therefore
+ * captured once into a CUDA graph and replayed; everything the kernels read that varies
+ * from step to step (dt, t, max |u|, the forcing box) already lives in device memory.
+ */
+#ifndef NSB_EMULATE
+static void graph_make_key(const nsb_ctx *c, unsigned char key[192]) {
+    memset(key, 0, 192);
+    size_t o = 0;
+    auto put = [&](const void *p, size_t n) { memcpy(key + o, p, n); o += n; };
+    put(&c->hv, sizeof(c->hv));
+    put(&c->prm.Re, sizeof(double));
+    put(&c->prm.cfl_factor, sizeof(double));
+    const int ints[8] = {c->force_on, c->ib, c->jb, c->masked_nonzero, c->fast, c->chain_mode, c->mg_world, c->k_truth};
+    put(ints, sizeof(ints));
+    const void *ptrs[6] = {c->d_force, c->kSFD, c->kW0, c->kWst, c->kACC, c->bufP};
+    put(ptrs, sizeof(ptrs));
+}
+#endif
+
+extern "C" int nsb_rk4_step(nsb_ctx *c, double dt) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->device));
+#ifndef NSB_EMULATE
+    const bool eligible = !(dt > 0.0) && c->mg_world == 1 && !c->prof_on && c->graph_mode != 0 &&
+                          (c->graph_mode > 0 || c->N <= (size_t)4096 * 4096);
+    if (eligible) {
+        /* the state layout the step works on must be current BEFORE the key is taken / the capture starts */
+        if (alpha_fast_ok(c)) { if (sync_k(c)) return -1; } else if (sync_ref(c)) return -1;
+        unsigned char key[192];
+        graph_make_key(c, key);
+        if (memcmp(key, c->graph_key, sizeof(key)) != 0) {
+            memcpy(c->graph_key, key, sizeof(key));
+            c->graph_warm = 0;
+            if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+        }
+        if (c->graph_exec) {
+            CK(cudaGraphLaunch(c->graph_exec, c->stream));
+            c->launches += c->graph_launches;
+            return 0;
+        }
+        if (c->graph_warm >= 1) { /* one plain step has done every lazy allocation / attribute call: capture now */
+            const long long l0 = c->launches;
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = rk4_step_launch(c, dt);
+            const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            if (rc != 0 || e != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                c->launches = l0;
+                c->graph_mode = 0; /* not capturable here: plain launches from now on */
+                if (rc != 0) return -1;
+                return rk4_step_launch(c, dt);
+            }
+            c->graph_launches = c->launches - l0;
+            c->launches = l0;
+            const cudaError_t ei = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ei != cudaSuccess) {
+                cudaGetLastError();
+                c->graph_exec = nullptr;
+                c->graph_mode = 0;
+                return rk4_step_launch(c, dt);
+            }
+            CK(cudaGraphLaunch(c->graph_exec, c->stream));
+            c->launches += c->graph_launches;
+            return 0;
+        }
+        c->graph_warm += 1;
+    }
+#endif
+    return rk4_step_launch(c, dt);
+}
+
 extern "C" int nsb_diagnostics(nsb_ctx *c, double out[4]) {
     if (!c || !out) return fail("nsb_diagnostics: null argument");
     CK(cudaSetDevice(c->device));
@@ -1775,6 +1891,14 @@ extern "C" int nsb_get_state(nsb_ctx *c, double *dt, double *t, int *steps) {
     if (t) *t = c->h_sc->t;
     if (steps) *steps = c->h_sc->step;
     return 0;
+}
+
+extern "C" int nsb_check_finite(nsb_ctx *c, int *step_out) {
+    if (!c) return fail("null context");
+    CK(cudaSetDevice(c->device));
+    if (fetch_scalars(c)) return -1;
+    if (step_out) *step_out = c->h_sc->nonfinite ? c->h_sc->nonfinite_step : -1;
+    return c->h_sc->nonfinite ? 1 : 0;
 }
 
 extern "C" int nsb_set_time(nsb_ctx *c, double t) {

@@ -66,6 +66,12 @@ struct NsbRk {
     int ib, jb;
 };
 
+/* max that keeps a NaN once it has seen one (fmax drops NaNs): a blown-up field must not turn into
+ * "max |u| = 0, dt = MAX_DT" (what /root/reference/src/spectral/spectral_time_integration.c:14-20 does with its
+ * `if (vel > max_vel)`); as ordered bits NaN and +Inf compare above every finite value, so the atomicMax of the
+ * reduction carries the flag to the CFL kernel */
+__device__ __forceinline__ double nsb_max_sticky(double a, double b) { return (b > a || b != b) ? b : a; }
+
 __device__ __forceinline__ int nsb_band(int j, int ny) { return (j <= ny / 2) ? j : j - ny; }
 __device__ __forceinline__ int nsb_iabs(int a) { return a < 0 ? -a : a; }
 
@@ -496,8 +502,7 @@ __device__ __forceinline__ void nsb_block_max_to_global(double v, unsigned long 
     __syncthreads();
     for (int st = blockDim.x >> 1; st > 0; st >>= 1) {
         if ((int)threadIdx.x < st) {
-            const double o = red[threadIdx.x + st];
-            if (o > red[threadIdx.x]) red[threadIdx.x] = o;
+            red[threadIdx.x] = nsb_max_sticky(red[threadIdx.x], red[threadIdx.x + st]);
         }
         __syncthreads();
     }
@@ -573,7 +578,7 @@ __global__ void __launch_bounds__(256) k_gamma(NsbGeom g, GammaArgs a) {
             /* spectral_time_integration.c:16 : |u|^2 = psi_y^2 + psi_x^2 */
             const double m0 = __dadd_rn(__dmul_rn(a0.y, a0.y), __dmul_rn(a0.x, a0.x));
             const double m1 = __dadd_rn(__dmul_rn(a1.y, a1.y), __dmul_rn(a1.x, a1.x));
-            umax = fmax(umax, fmax(m0, m1));
+            umax = nsb_max_sticky(umax, nsb_max_sticky(m0, m1));
             s[p] = cmk(J0, J1);
         }
         __syncthreads();
@@ -593,7 +598,7 @@ __global__ void __launch_bounds__(256) k_gamma(NsbGeom g, GammaArgs a) {
                     if (a.phys_out[2 * pp + 1] != nullptr) a.phys_out[2 * pp + 1][o] = z.y;
                     sq[2 * pp + 1] += z.y * z.y;
                 }
-                if (pp == 0) umax = fmax(umax, __dadd_rn(__dmul_rn(z.x, z.x), __dmul_rn(z.y, z.y)));
+                if (pp == 0) umax = nsb_max_sticky(umax, __dadd_rn(__dmul_rn(z.x, z.x), __dmul_rn(z.y, z.y)));
             }
         }
         __syncthreads();
@@ -712,11 +717,17 @@ struct NsbScalars {
     double dt_hist[256];
     unsigned peer_flags[8];        /* device barrier of the slab decomposition: epoch announced by each peer */
     double stats[8];               /* nsb_spectral_stats accumulators */
+    unsigned nonfinite;            /* set by the CFL kernel when max |u|^2 is NaN or Inf */
+    int nonfinite_step;            /* step counter at that moment */
 };
 
 /* spectral_time_integration.c:22-30 : dt = clamp(min(cfl*dx/(|u|max+1e-12), 0.5*Re*dx^2)) */
 __global__ void k_cfl_dt(NsbScalars *sc, double cfl, double dx_min, double Re, double min_dt, double max_dt) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (sc->umax_bits >= 0x7FF0000000000000ull && !sc->nonfinite) {
+        sc->nonfinite = 1u;
+        sc->nonfinite_step = sc->step;
+    }
     const double max_vel = __dsqrt_rn(__longlong_as_double((long long)sc->umax_bits));
     const double dt_cfl = __ddiv_rn(__dmul_rn(cfl, dx_min), __dadd_rn(max_vel, 1e-12));
     const double dt_visc = __dmul_rn(__dmul_rn(__dmul_rn(0.5, Re), dx_min), dx_min);
@@ -739,6 +750,10 @@ __global__ void k_cfl_dt_multi(NsbScalars *sc, NsbPeerScalars ps, int world, dou
     for (int p = 0; p < world; ++p) {
         const unsigned long long b = *reinterpret_cast<volatile unsigned long long *>(&ps.sc[p]->umax_bits);
         if (b > bits) bits = b;
+    }
+    if (bits >= 0x7FF0000000000000ull && !sc->nonfinite) {
+        sc->nonfinite = 1u;
+        sc->nonfinite_step = sc->step;
     }
     const double max_vel = __dsqrt_rn(__longlong_as_double((long long)bits));
     const double dt_cfl = __ddiv_rn(__dmul_rn(cfl, dx_min), __dadd_rn(max_vel, 1e-12));
@@ -875,7 +890,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gamma1024(NsbGeom g, GammaFas
                 const cd z1 = P[m * 32 + lane], z2 = x[m];
                 /* spectral_core.c:103 and spectral_time_integration.c:16 */
                 const double J = __dsub_rn(__dmul_rn(z1.x, z2.y), __dmul_rn(z1.y, z2.x));
-                umax = fmax(umax, __dadd_rn(__dmul_rn(z1.y, z1.y), __dmul_rn(z1.x, z1.x)));
+                umax = nsb_max_sticky(umax, __dadd_rn(__dmul_rn(z1.y, z1.y), __dmul_rn(z1.x, z1.x)));
                 if (comb == 0) PJ[m * 32 + lane] = J;
                 else x[m] = cmk(PJ[m * 32 + lane], J);
             }
@@ -898,7 +913,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_gamma1024(NsbGeom g, GammaFas
     }
     if (a.umax_bits != nullptr) {
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, off));
+        for (int off = 16; off > 0; off >>= 1) umax = nsb_max_sticky(umax, __shfl_xor_sync(0xffffffffu, umax, off));
         if (lane == 0) atomicMax(a.umax_bits, (unsigned long long)__double_as_longlong(umax));
     }
 }

@@ -563,6 +563,17 @@ int ns_spectral_run_steps(NSSpectralData *d, int n, NSForcingState *fs) {
     (void)group;
     int steps = 0;
     NSB_OK(nsb_get_state(b->ctx, &d->dt, &d->t, &steps), W);
+    /* a blown-up field is reported, not integrated on with dt = MAX_DT */
+    int bad_step = -1;
+    for (int r = 0; r < (b->ngpus > 1 ? b->ngpus : 1); ++r) {
+        const int bad = nsb_check_finite(b->ngpus > 1 ? b->group[r] : b->ctx, &bad_step);
+        if (bad < 0) die(W, nsb_last_error());
+        if (bad) {
+            set_error("%s: the velocity field is no longer finite (NaN/Inf seen by the CFL reduction at step %d)", W,
+                      bad_step);
+            return -1;
+        }
+    }
     if (!lazy(d)) {
         download(d, NSB_OMEGA_HAT, d->omega_hat, W);
         if (sfd) download(d, NSB_SFD_HAT, d->sfd_hat, W);

@@ -250,6 +250,34 @@ def _spectrum_and_strided_output(lib, tmp_path):
     s.close()
 
 
+def _blowup_is_reported(lib, n):
+    """a NaN in the field is carried through the fused max|u| reduction to the CFL kernel and
+    ns_spectral_run_steps fails loudly instead of integrating on with dt = MAX_DT like the reference would."""
+    s = hostlib.Solver(lib, n, n, Re=500.0)
+    lib.ns_spectral_initialize_random_phase(s.sp, 3, 6.0, 3.0)
+    lib.ns_spectral_set_sync_policy(s.sp, 1)
+    assert lib.ns_spectral_run_steps(s.sp, 2, None) == 0
+    lib.ns_spectral_sync_to_host(s.sp, 0x1)                      # NS_FIELD_OMEGA_HAT
+    s.arr("omega_hat")[2, 1] = complex(np.nan, 0.0)
+    lib.ns_spectral_sync_to_device(s.sp, 0x1)
+    assert lib.ns_spectral_run_steps(s.sp, 3, None) == -1
+    assert b"no longer finite" in lib.ns_spectral_last_error()
+    # a fresh, finite state clears the verdict
+    lib.ns_spectral_initialize_random_phase(s.sp, 3, 6.0, 3.0)
+    assert lib.ns_spectral_run_steps(s.sp, 1, None) == 0
+    s.close()
+
+
+def test_blowup_is_reported_emu(emu_host):
+    _blowup_is_reported(emu_host, 32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [64, 2048])
+def test_blowup_is_reported_gpu(gpu_host, n):
+    _blowup_is_reported(gpu_host, n)
+
+
 def test_reference_unit_tests_emu(emu_host):
     _reference_unit_tests(emu_host)
 
