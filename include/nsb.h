@@ -82,6 +82,9 @@ int nsb_sync(nsb_ctx *c);
 int nsb_upload(nsb_ctx *c, int field, const void *host);
 int nsb_download(nsb_ctx *c, int field, void *host);
 int nsb_zero(nsb_ctx *c, int field);
+/* the columns [col0, col1) this device owns (all of the retained ones on a single device) of a spectral field as a
+ * dense ny x (col1 - col0) host block: what a per-device restart file of a slab-decomposed run holds */
+int nsb_download_columns(nsb_ctx *c, int field, void *host, int *col0, int *col1);
 int nsb_copy(nsb_ctx *c, int dst_field, int src_field);
 
 /* ns_spectral_hyperviscosity_set (hyperviscosity.c:32-58): parameters only; weights are
@@ -122,6 +125,14 @@ int nsb_cfl_timestep(nsb_ctx *c, double *dt_out);
  * never visits the host. */
 int nsb_rk4_step(nsb_ctx *c, double dt);
 
+/* The same step in two halves with the device's CFL step size returned in between (8 bytes device -> host), for
+ * coloured forcing, whose generator needs dt before it consumes its stream (src/common/forcing.c:138-147):
+ * begin runs stage 1's transforms, the fused max |u| and the CFL kernel and returns dt; the caller sets the forcing;
+ * finish runs the RK updates and stages 2-4. ctxs: one context, or the contexts of a single-process device group.
+ * Fast path only (grids with Y1 == X2 == 1024): otherwise begin returns < 0 and nothing has been launched. */
+int nsb_rk4_step_begin(nsb_ctx **ctxs, int n, double *dt_out);
+int nsb_rk4_step_finish(nsb_ctx **ctxs, int n);
+
 /* out[0..2] = sum u^2, sum v^2, sum omega^2 over the grid, out[3] = max(u^2+v^2), from
  * OMEGA_HAT (ns_spectral_compute_energy/_enstrophy, spectral_analysis.c:8-33, without
  * materialising the fields). Synchronous. */
@@ -132,12 +143,14 @@ int nsb_diagnostics_phys(nsb_ctx *c, double out[4]);
 /* The reductions over OMEGA_HAT that ns_spectral_check_resolution (spectral_analysis.c:36-66) and
  * ns_spectral_analyze_convergence (:69-100) make, on the device: out = { sum |w|^2, sum |w|^2 over
  * sqrt(k2)/sqrt(k2_last) > 0.8, max |w|, sum |w|^2 over k2 > 0.25 k2_last, number of such modes,
- * k2_last } with k2_last = k2[nkx*nky - 1] as in the reference. Synchronous. */
+ * k2_last } with k2_last = k2[nkx*nky - 1] as in the reference. Synchronous. On a context of a slab-decomposed
+ * group the sums run over the device's own columns only: add the sums (take the max of out[2]) of all devices. */
 int nsb_spectral_stats(nsb_ctx *c, double out[6]);
 
 /* ns_spectral_analyze_spectrum (spectral_analysis.c:103-142) without downloading omega_hat, u_hat,
  * v_hat: ek_sum[b] = sum of 0.5 (|u_hat|^2 + |v_hat|^2) and count[b] = number of modes over the
- * shell b = (int)(sqrt(k2) + 0.5), b < nbins (host arrays of nbins entries). Synchronous. */
+ * shell b = (int)(sqrt(k2) + 0.5), b < nbins (host arrays of nbins entries). Synchronous. Own columns only on a
+ * context of a slab-decomposed group (add the arrays of all devices). */
 int nsb_energy_spectrum(nsb_ctx *c, int nbins, double *ek_sum, int *count);
 
 /* Re and cfl_factor are read live from NSSpectralData by the reference (spectral_time_integration.c:

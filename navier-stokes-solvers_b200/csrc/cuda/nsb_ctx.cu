@@ -123,6 +123,7 @@ struct nsb_ctx {
     int sm_count;
     long long launches;
     /* CUDA-graph replay of the device-dt step on launch-bound (small) grids */
+    int cfl_done;              /* nsb_rk4_step_begin has already launched this step's CFL kernel */
     int graph_mode;            /* NSB_GRAPH: -1 automatic (grids up to 4096^2), 0 off, 1 always */
     int graph_warm;            /* consecutive plain steps taken with the current key */
     long long graph_launches;  /* kernels inside the captured step */
@@ -241,6 +242,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->smem_set = new std::map<const void *, size_t>();
     c->launches = 0;
     c->graph_mode = getenv("NSB_GRAPH") ? atoi(getenv("NSB_GRAPH")) : -1;
+    c->cfl_done = 0;
     c->graph_warm = 0;
     c->graph_launches = 0;
     memset(c->graph_key, 0, sizeof(c->graph_key));
@@ -614,6 +616,25 @@ extern "C" int nsb_download(nsb_ctx *c, int field, void *host) {
     if (get_field(c, field, &d)) return -1;
     const size_t bytes = field_is_phys(field) ? c->N * sizeof(double) : c->M * sizeof(cd);
     CK(cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+/* own-column block [col0, col1) x ny of a spectral field <-> a dense host buffer (per-device restart files of a
+ * slab-decomposed run: no gather through the first device) */
+extern "C" int nsb_download_columns(nsb_ctx *c, int field, void *host, int *col0, int *col1) {
+    if (!c || !host) return fail("nsb_download_columns: null argument");
+    if (!field_is_hat(field)) return fail("nsb_download_columns: not a spectral field");
+    CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
+    void *d;
+    if (get_field(c, field, &d)) return -1;
+    const int w = c->mg_c1 - c->mg_c0;
+    if (col0) *col0 = c->mg_c0;
+    if (col1) *col1 = c->mg_c1;
+    if (w <= 0) return 0;
+    CK(cudaMemcpy2DAsync(host, (size_t)w * sizeof(cd), (const cd *)d + c->mg_c0, (size_t)c->g.nkx * sizeof(cd),
+                         (size_t)w * sizeof(cd), (size_t)c->g.ny, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1540,7 +1561,8 @@ static int fast_phase(nsb_ctx *c, int ph, double dt) {
         return launch_chain(c, device_dt && ph == 1);
     }
     const int stage = ph / 2;
-    if (stage == 1 && device_dt && launch_cfl(c)) return -1;
+    if (stage == 1 && device_dt && !c->cfl_done && launch_cfl(c)) return -1;
+    c->cfl_done = 0;
     AlphaFastArgs fa;
     memset(&fa, 0, sizeof(fa));
     fill_alpha_fast(c, fa, c->bufTp, c->mg_cb);
@@ -2080,6 +2102,46 @@ extern "C" int nsb_mgpu_group_step(nsb_ctx **cs, int n, double dt) {
     return 0;
 }
 
+/*
+ * The step in two halves with the CFL step size handed to the host in between (8 bytes): coloured forcing needs
+ * dt BEFORE the stream is consumed (/root/reference/src/common/forcing.c:138-147) but the device only knows it
+ * after stage 1's physical-space kernel. begin = stage-1 transforms + max|u| + CFL kernel (phases 0-1), returns dt;
+ * the caller generates the forcing, nsb_set_forcing()s it, then finish = the RK updates and stages 2-4.
+ * One context (n == 1) or a single-process device group; fast path only (otherwise < 0 and nothing was launched).
+ */
+extern "C" int nsb_rk4_step_begin(nsb_ctx **cs, int n, double *dt_out) {
+    if (!cs || n < 1 || n > NSB_MAXP || !dt_out) return fail("nsb_rk4_step_begin: bad arguments");
+    for (int i = 0; i < n; ++i)
+        if (!cs[i] || !fast_chain_ok(cs[i]) || cs[i]->mg_world != n || (n > 1 && cs[i]->mg_ipc))
+            return fail("nsb_rk4_step_begin: context %d is not on the (slab-decomposed) fast path", i);
+    for (int ph = 0; ph < 2; ++ph) {
+        for (int i = 0; i < n; ++i)
+            if (fast_phase(cs[i], ph, 0.0)) return -1;
+        if (n > 1 && group_barrier(cs, n)) return -1;
+    }
+    for (int i = 0; i < n; ++i) {
+        CK(cudaSetDevice(cs[i]->device));
+        if (launch_cfl(cs[i])) return -1;
+        cs[i]->cfl_done = 1;
+    }
+    CK(cudaSetDevice(cs[0]->device));
+    if (fetch_scalars(cs[0])) return -1;
+    *dt_out = cs[0]->h_sc->dt;
+    return 0;
+}
+
+extern "C" int nsb_rk4_step_finish(nsb_ctx **cs, int n) {
+    if (!cs || n < 1 || n > NSB_MAXP) return fail("nsb_rk4_step_finish: bad arguments");
+    for (int i = 0; i < n; ++i)
+        if (!cs[i] || !cs[i]->cfl_done) return fail("nsb_rk4_step_finish: no step in progress on context %d", i);
+    for (int ph = 2; ph < NSB_FAST_PHASES; ++ph) {
+        for (int i = 0; i < n; ++i)
+            if (fast_phase(cs[i], ph, 0.0)) return -1;
+        if (n > 1 && ph + 1 < NSB_FAST_PHASES && group_barrier(cs, n)) return -1;
+    }
+    return 0;
+}
+
 /* Single-process group: make cs[0]'s reference-layout OMEGA_HAT (and SFD_HAT) complete and current
  * from the own-column blocks of all devices, so that every single-device entry point
  * (diagnostics, transforms, download) can run on cs[0]. The other devices keep their own
@@ -2191,19 +2253,20 @@ extern "C" int nsb_state_checksum(nsb_ctx *c, unsigned long long out[2]) {
  * reductions over omega_hat; computed here so a LAZY-mode driver loop never downloads the field.
  * out = { sum |w|^2, sum |w|^2 over sqrt(k2)/sqrt(k2_last) > 0.8, max |w|,
  *         sum |w|^2 over k2 > 0.25 k2_last, number of such modes, k2_last } */
-__global__ void __launch_bounds__(256) k_spectral_stats(NsbGeom g, const cd *W, double *acc,
-                                                        unsigned long long *maxbits, unsigned long long *count) {
+__global__ void __launch_bounds__(256) k_spectral_stats(NsbGeom g, const cd *W, int ca, int cb, double *acc,
+                                                        unsigned long long *maxbits) {
     NSB_DYN_SMEM(double, red);
-    const size_t M = (size_t)g.nkx * g.ny;
+    const int w = cb - ca;
+    const size_t total = (size_t)w * g.ny;
     const double kxl = g.kx[g.nkx - 1], kyl = g.ky[g.ny - 1];
     const double k2_last = __dadd_rn(__dmul_rn(kxl, kxl), __dmul_rn(kyl, kyl));
     const double max_k = __dsqrt_rn(k2_last);
     double tot = 0.0, high = 0.0, peak = 0.0, tail = 0.0;
     unsigned long long cnt = 0ull;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M; idx += (size_t)gridDim.x * blockDim.x) {
-        const int j = (int)(idx / g.nkx), i = (int)(idx - (size_t)j * g.nkx);
-        const cd w = W[idx];
-        const double mag = hypot(w.x, w.y);
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(k / w), i = ca + (int)(k - (size_t)j * w);
+        const cd v = W[(size_t)j * g.nkx + i];
+        const double mag = hypot(v.x, v.y);
         const double mag2 = __dmul_rn(mag, mag);
         const double kxv = g.kx[i], kyv = g.ky[j];
         const double k2 = __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv));
@@ -2218,8 +2281,17 @@ __global__ void __launch_bounds__(256) k_spectral_stats(NsbGeom g, const cd *W, 
     nsb_block_sum_to_global(tail, acc + 2, red);
     nsb_block_sum_to_global((double)cnt, acc + 3, red);
     nsb_block_max_to_global(peak, maxbits, red);
-    (void)count;
     if (blockIdx.x == 0 && threadIdx.x == 0) acc[4] = k2_last;
+}
+
+/* columns a reduction over omega_hat covers on this context: everything on a single device; on a device of a
+ * slab-decomposed group its own block (the last device also takes the masked columns beyond the retained set,
+ * which are zero but count as modes), so that the partial results of all devices add up to the whole */
+static void reduction_columns(const nsb_ctx *c, int *ca, int *cb) {
+    if (c->mg_world <= 1) { *ca = 0; *cb = c->g.nkx; return; }
+    *ca = c->mg_c0;
+    *cb = (c->mg_rank == c->mg_world - 1) ? c->g.nkx : c->mg_c1;
+    if (*cb < *ca) *cb = *ca;
 }
 
 extern "C" int nsb_spectral_stats(nsb_ctx *c, double out[6]) {
@@ -2231,11 +2303,15 @@ extern "C" int nsb_spectral_stats(nsb_ctx *c, double out[6]) {
     CK(cudaMemsetAsync(c->d_sc->sums, 0, sizeof(double) * 4, c->stream));
     CK(cudaMemsetAsync(&c->d_sc->umax_bits, 0, sizeof(unsigned long long), c->stream));
     CK(cudaMemsetAsync(c->d_sc->stats, 0, sizeof(c->d_sc->stats), c->stream));
-    auto k = k_spectral_stats;
-    NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 256 * sizeof(double), c->stream, c->g, (const cd *)w,
-               c->d_sc->stats, &c->d_sc->umax_bits, (unsigned long long *)nullptr);
-    CKL();
-    c->launches++;
+    int ca, cb;
+    reduction_columns(c, &ca, &cb);
+    if (cb > ca) {
+        auto k = k_spectral_stats;
+        NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 256 * sizeof(double), c->stream, c->g, (const cd *)w, ca, cb,
+                   c->d_sc->stats, &c->d_sc->umax_bits);
+        CKL();
+        c->launches++;
+    }
     if (fetch_scalars(c)) return -1;
     double peak;
     memcpy(&peak, &c->h_sc->umax_bits, sizeof(double));
@@ -2250,16 +2326,17 @@ extern "C" int nsb_spectral_stats(nsb_ctx *c, double out[6]) {
  * (psi_hat, u_hat, v_hat per mode as in spectral_core.c:8-34; nothing is materialised or downloaded).
  * A warp covers 32 consecutive kx of one ky row, where the shell index is non-decreasing: equal
  * neighbours are combined by a segmented shuffle scan, so one atomic per (warp, shell) reaches L2. */
-__global__ void __launch_bounds__(256) k_energy_spectrum(NsbGeom g, const cd *W, int nbins, double *ek, int *cnt) {
+__global__ void __launch_bounds__(256) k_energy_spectrum(NsbGeom g, const cd *W, int ca, int cb, int nbins, double *ek,
+                                                         int *cnt) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    const int chunks = (g.nkx + 31) >> 5;
+    const int chunks = (cb - ca + 31) >> 5;
     const size_t nwork = (size_t)g.ny * chunks;
     for (size_t wk = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); wk < nwork; wk += (size_t)gridDim.x * wpb) {
-        const int j = (int)(wk / chunks), i = (int)(wk - (size_t)j * chunks) * 32 + lane;
+        const int j = (int)(wk / chunks), i = ca + (int)(wk - (size_t)j * chunks) * 32 + lane;
         int bin = -1;
         double e = 0.0;
-        if (i < g.nkx) {
+        if (i < cb) {
             const double kxv = g.kx[i], kyv = g.ky[j];
             const double k2 = __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv));
             const int b = (int)(__dsqrt_rn(k2) + 0.5);
@@ -2302,8 +2379,10 @@ extern "C" int nsb_energy_spectrum(nsb_ctx *c, int nbins, double *ek_sum, int *c
     int *d_cnt = reinterpret_cast<int *>(d_ek + nbins);
     cudaError_t e = cudaMemsetAsync(d_ek, 0, bytes, c->stream);
     if (e == cudaSuccess) {
+        int ca, cb;
+        reduction_columns(c, &ca, &cb);
         auto k = k_energy_spectrum;
-        NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 0, c->stream, c->g, (const cd *)w, nbins, d_ek, d_cnt);
+        if (cb > ca) NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 0, c->stream, c->g, (const cd *)w, ca, cb, nbins, d_ek, d_cnt);
         e = cudaGetLastError();
         c->launches++;
     }

@@ -552,6 +552,20 @@ int ns_spectral_run_steps(NSSpectralData *d, int n, NSForcingState *fs) {
              * evaluated first (on a group: from the state gathered into the first device, 8 bytes back) and
              * handed to the step, exactly the reference's `data->dt = cfl(); advance_rk4()` order */
             if (fs->config.type == NS_FORCING_COLORED_NOISE) {
+                /* fast path: the step is split around the device's own CFL kernel (8 bytes back), on one device or
+                 * on a group; other grids evaluate the CFL step in a separate pass over omega_hat first */
+                nsb_ctx **cs = group ? b->group : &b->ctx;
+                if (group && b->dirty) {
+                    NSB_OK(nsb_mgpu_group_scatter(b->group, b->ngpus), W);
+                    b->dirty = 0;
+                }
+                if (nsb_rk4_step_begin(cs, group ? b->ngpus : 1, &dt) == 0) {
+                    ns_forcing_generate_box(fs, dt, b->forcing_idx, b->ib, b->jb, b->forcing_box);
+                    set_forcing_all(d, b->ib, b->jb, (const double *)b->forcing_box, W);
+                    NSB_OK(nsb_rk4_step_finish(cs, group ? b->ngpus : 1), W);
+                    if (group) b->gathered = 0;
+                    continue;
+                }
                 c = ctx_ro(d, W);
                 NSB_OK(nsb_cfl_timestep(c, &dt), W);
             }
@@ -623,7 +637,26 @@ static void lazy_fetch_spectra(NSSpectralData *d, int with_velocity, const char 
 /* spectral_analysis.c:36-66 */
 /* reductions over omega_hat for the two driver-loop diagnostics: on the device in LAZY mode (no
  * field download), over the host array otherwise */
+/* a device group that has stepped since the last gather: reductions over omega_hat run as partial sums on every
+ * device (own columns) and are combined here; nothing is gathered into the first device */
+static int group_partial(const NSSpectralData *d) {
+    const Backend *b = backend_of(d);
+    return b && b->ctx && b->policy == NS_SYNC_LAZY && b->ngpus > 1 && !b->gathered && !b->dirty;
+}
+
 static void omega_hat_stats(NSSpectralData *d, double out[6], const char *where) {
+    if (group_partial(d)) {
+        Backend *b = backend_of(d);
+        for (int k = 0; k < 6; ++k) out[k] = 0.0;
+        for (int r = 0; r < b->ngpus; ++r) {
+            double part[6];
+            NSB_OK(nsb_spectral_stats(b->group[r], part), where);
+            out[0] += part[0]; out[1] += part[1]; out[3] += part[3]; out[4] += part[4];
+            if (part[2] > out[2]) out[2] = part[2];
+            out[5] = part[5];
+        }
+        return;
+    }
     if (lazy(d)) {
         NSB_OK(nsb_spectral_stats(ctx_ro(d, where), out), where);
         return;
@@ -650,7 +683,7 @@ static void omega_hat_stats(NSSpectralData *d, double out[6], const char *where)
 
 int ns_spectral_check_resolution(NSSpectralData *d) {
     static const char *W = "ns_spectral_check_resolution";
-    ctx_ro(d, W);
+    if (!group_partial(d)) ctx_ro(d, W);
     double st[6];
     omega_hat_stats(d, st, W);
     const double frac = (st[0] > 1e-16) ? st[1] / st[0] : 0.0;
@@ -682,6 +715,21 @@ void ns_spectral_analyze_convergence(NSSpectralData *d, int step) {
 int ns_spectral_energy_spectrum(NSSpectralData *d, int nbins, double *ek_sum, int *count) {
     static const char *W = "ns_spectral_energy_spectrum";
     if (!d || nbins <= 0 || !ek_sum || !count) return -1;
+    if (group_partial(d)) {
+        Backend *b = backend_of(d);
+        double *ek = (double *)malloc((size_t)nbins * sizeof(double));
+        int *cn = (int *)malloc((size_t)nbins * sizeof(int));
+        if (!ek || !cn) { free(ek); free(cn); return -1; }
+        memset(ek_sum, 0, (size_t)nbins * sizeof(double));
+        memset(count, 0, (size_t)nbins * sizeof(int));
+        for (int r = 0; r < b->ngpus; ++r) {
+            NSB_OK(nsb_energy_spectrum(b->group[r], nbins, ek, cn), W);
+            for (int k = 0; k < nbins; ++k) { ek_sum[k] += ek[k]; count[k] += cn[k]; }
+        }
+        free(ek);
+        free(cn);
+        return 0;
+    }
     if (lazy(d)) {
         NSB_OK(nsb_energy_spectrum(ctx_ro(d, W), nbins, ek_sum, count), W);
         return 0;
@@ -701,7 +749,7 @@ int ns_spectral_energy_spectrum(NSSpectralData *d, int nbins, double *ek_sum, in
 
 void ns_spectral_analyze_spectrum(NSSpectralData *d) {
     static const char *W = "ns_spectral_analyze_spectrum";
-    ctx_ro(d, W);
+    if (!group_partial(d)) ctx_ro(d, W);
     const int nkx = d->nkx, nky = d->nky;
     const int max_k = (int)fmin(nkx, nky / 2);
     double *ek = (double *)calloc((size_t)max_k, sizeof(double));
@@ -904,17 +952,88 @@ static int read_all(FILE *fp, void *p, size_t bytes) {
     return 0;
 }
 
+/* <filename>.rank<r>: NSSlabHeader | omega_hat[ny][c1-c0] | sfd_hat[ny][c1-c0] if has_sfd */
+typedef struct {
+    char magic[8]; /* "NSBSLB1\0" */
+    int rank, nranks, col0, col1, ny, has_sfd;
+} NSSlabHeader;
+
+static int save_slab_file(NSSpectralData *d, nsb_ctx *c, int rank, int nranks, int sfd, const char *filename) {
+    char path[1024];
+    snprintf(path, sizeof path, "%s.rank%d", filename, rank);
+    const size_t cap = ((size_t)d->nkx / (size_t)nranks + 16) * (size_t)d->nky * sizeof(fftw_complex);
+    void *buf = malloc(cap);
+    if (!buf) return -1;
+    NSSlabHeader sh;
+    memset(&sh, 0, sizeof sh);
+    memcpy(sh.magic, "NSBSLB1", 8);
+    sh.rank = rank; sh.nranks = nranks; sh.ny = d->nky; sh.has_sfd = sfd;
+    int rc = nsb_download_columns(c, NSB_OMEGA_HAT, buf, &sh.col0, &sh.col1);
+    FILE *fp = rc == 0 ? fopen(path, "wb") : NULL;
+    if (!fp) { free(buf); return -1; }
+    const size_t bytes = (size_t)(sh.col1 - sh.col0) * (size_t)d->nky * sizeof(fftw_complex);
+    rc = write_all(fp, &sh, sizeof sh);
+    if (rc == 0) rc = write_all(fp, buf, bytes);
+    if (rc == 0 && sfd) {
+        rc = nsb_download_columns(c, NSB_SFD_HAT, buf, NULL, NULL);
+        if (rc == 0) rc = write_all(fp, buf, bytes);
+    }
+    if (fclose(fp) != 0) rc = -1;
+    free(buf);
+    return rc;
+}
+
+/* the slab files of a per-device restart back into the host arrays (any device count may resume from them) */
+static int load_slab_files(NSSpectralData *d, int nranks, int has_sfd, const char *filename) {
+    memset(d->omega_hat, 0, n_spec(d) * sizeof(fftw_complex));
+    if (has_sfd) memset(d->sfd_hat, 0, n_spec(d) * sizeof(fftw_complex));
+    for (int r = 0; r < nranks; ++r) {
+        char path[1024];
+        snprintf(path, sizeof path, "%s.rank%d", filename, r);
+        FILE *fp = fopen(path, "rb");
+        if (!fp) return -1;
+        NSSlabHeader sh;
+        int rc = read_all(fp, &sh, sizeof sh);
+        if (rc != 0 || memcmp(sh.magic, "NSBSLB1", 8) != 0 || sh.rank != r || sh.nranks != nranks || sh.ny != d->nky ||
+            sh.col0 < 0 || sh.col1 > d->nkx || sh.col1 < sh.col0 || (has_sfd && !sh.has_sfd)) {
+            fclose(fp);
+            return -1;
+        }
+        const int w = sh.col1 - sh.col0;
+        fftw_complex *row = (fftw_complex *)malloc((size_t)(w > 0 ? w : 1) * sizeof(fftw_complex));
+        if (!row) { fclose(fp); return -1; }
+        for (int pass = 0; pass < (has_sfd ? 2 : 1) && rc == 0; ++pass) {
+            fftw_complex *dst = pass ? d->sfd_hat : d->omega_hat;
+            for (int j = 0; j < d->nky && rc == 0; ++j) {
+                rc = read_all(fp, row, (size_t)w * sizeof(fftw_complex));
+                if (rc == 0) memcpy(dst + (size_t)j * d->nkx + sh.col0, row, (size_t)w * sizeof(fftw_complex));
+            }
+        }
+        free(row);
+        fclose(fp);
+        if (rc != 0) return -1;
+    }
+    return 0;
+}
+
 int ns_spectral_save_state(NSSpectralData *d, const NSForcingState *fs, const char *filename) {
     static const char *W = "ns_spectral_save_state";
     if (!d || !filename) { set_error("%s: NULL argument", W); return -1; }
-    ctx_ro(d, W);
+    Backend *bk = backend_of(d);
+    if (!bk || !bk->ctx) { set_error("%s: no device context", W); return -1; }
     const NSSpectralHyperviscosityConfig *h = &d->hyperviscosity;
     const int sfd = (h->sfd_enabled && h->sfd_strength > 0.0);
+    /* a slab-decomposed group that has stepped since the last gather: every device writes its own column
+     * block to <filename>.rank<r> (per-GPU slab files), nothing funnels through device 0 */
+    const int per_device = lazy(d) && bk->ngpus > 1 && !bk->gathered && !bk->dirty;
+    if (!per_device) ctx_ro(d, W);
     if (lazy(d)) { /* the device copy is the truth */
-        download(d, NSB_OMEGA_HAT, d->omega_hat, W);
-        if (sfd) download(d, NSB_SFD_HAT, d->sfd_hat, W);
+        if (!per_device) {
+            download(d, NSB_OMEGA_HAT, d->omega_hat, W);
+            if (sfd) download(d, NSB_SFD_HAT, d->sfd_hat, W);
+        }
         int steps;
-        NSB_OK(nsb_get_state(ctx_ro(d, W), &d->dt, &d->t, &steps), W);
+        NSB_OK(nsb_get_state(bk->ctx, &d->dt, &d->t, &steps), W);
     }
     NSRestartHeader hd;
     memset(&hd, 0, sizeof hd);
@@ -941,12 +1060,17 @@ int ns_spectral_save_state(NSSpectralData *d, const NSForcingState *fs, const ch
         hd.have_spare = fs->have_spare;
         hd.active_modes = fs->active_modes;
     }
+    hd.pad_ = per_device ? bk->ngpus : 0; /* number of per-device slab files that hold the fields (0: in this file) */
     FILE *fp = fopen(filename, "wb");
     if (!fp) { set_error("%s: cannot open %s", W, filename); return -1; }
     const size_t mb = n_spec(d) * sizeof(fftw_complex);
     int rc = write_all(fp, &hd, sizeof hd);
-    if (rc == 0) rc = write_all(fp, d->omega_hat, mb);
-    if (rc == 0 && hd.has_sfd) rc = write_all(fp, d->sfd_hat, mb);
+    if (per_device) {
+        for (int r = 0; r < bk->ngpus && rc == 0; ++r) rc = save_slab_file(d, bk->group[r], r, bk->ngpus, sfd, filename);
+    } else {
+        if (rc == 0) rc = write_all(fp, d->omega_hat, mb);
+        if (rc == 0 && hd.has_sfd) rc = write_all(fp, d->sfd_hat, mb);
+    }
     if (rc == 0 && hd.has_colored) rc = write_all(fp, fs->colored_state, mb);
     if (fclose(fp) != 0) rc = -1;
     if (rc != 0) set_error("%s: short write to %s", W, filename);
@@ -985,8 +1109,14 @@ int ns_spectral_load_state(NSSpectralData *d, NSForcingState *fs, const char *fi
         return -1;
     }
     const size_t mb = n_spec(d) * sizeof(fftw_complex);
-    int rc = read_all(fp, d->omega_hat, mb);
-    if (rc == 0 && hd.has_sfd) rc = read_all(fp, d->sfd_hat, mb);
+    int rc = 0;
+    if (hd.pad_ > 1) { /* fields live in per-device slab files */
+        rc = load_slab_files(d, hd.pad_, hd.has_sfd, filename);
+        if (rc != 0) { fclose(fp); set_error("%s: cannot read the %d slab files %s.rank*", W, hd.pad_, filename); return -1; }
+    } else {
+        rc = read_all(fp, d->omega_hat, mb);
+        if (rc == 0 && hd.has_sfd) rc = read_all(fp, d->sfd_hat, mb);
+    }
     if (rc == 0 && hd.has_colored) {
         if (fs && hd.has_forcing) rc = read_all(fp, fs->colored_state, mb);
     }
