@@ -670,6 +670,117 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
     }
 }
 
+
+/* ------------------------------------------------ F, TMA-fed and persistent */
+
+/*
+ * Step 1 of F on TMA-landed boxes: A[row][cc] = P[pair row][kb + cc], M[row][cc'] = P[pair row][1024 - kb - (BC-1) + cc']
+ * (the mirror bins 1024 - k2 in ascending memory order, so bin 1024 - (kb + cc) sits at cc' = BC - 1 - cc), rows =
+ * the NP = R * X1 / 2 comb pairs of the slab. Same arithmetic as chain_F_step1 (bit-identical results).
+ */
+template <int X1>
+__device__ __forceinline__ void chain_F2_step1(const NsbGeom &g, const ChainArgs &a, cd *tile, const cd *A, const cd *M,
+                                               const cd *twtab, int kb) {
+    const int nseg = a.nd + a.nm;
+    const int bcs = nsb_log2i(g.BC);
+    for (int w = threadIdx.x; w < a.R * g.BC; w += blockDim.x) {
+        const int r = w >> bcs, cc = w & (g.BC - 1);
+        const int k2 = kb + cc;
+        cd x[X1];
+        if (k2 <= g.X2h) {
+#pragma unroll
+            for (int i = 0; i < X1 / 2; ++i) {
+                const int row = (r * X1) / 2 + i;
+                const cd Pk = A[row * g.BC + cc];
+                const cd Q = (k2 == 0) ? Pk : M[row * g.BC + (g.BC - 1 - cc)]; /* bin 1024 wraps to bin 0 */
+                const cd e = cmk(0.5 * (Pk.x + Q.x), 0.5 * (Pk.y - Q.y));
+                const cd o = cmk(0.5 * (Pk.y + Q.y), -0.5 * (Pk.x - Q.x));
+                x[2 * i] = cmul(e, twtab[cc * NSB_TWK_PITCH(X1) + 2 * i]);
+                x[2 * i + 1] = cmul(o, twtab[cc * NSB_TWK_PITCH(X1) + 2 * i + 1]);
+            }
+            nsb_dft<X1, false>(x);
+        } else {
+#pragma unroll
+            for (int x1 = 0; x1 < X1; ++x1) x[x1] = cmk(0.0, 0.0);
+        }
+#pragma unroll
+        for (int m = 0; m < X1; ++m) {
+            if (m < X1 / 2) {
+                if (m < a.nd) tile[(size_t)(r * nseg + m) * g.BC + cc] = x[m];
+            } else {
+                const int kp = X1 - 1 - m;
+                if (kp < a.nm) tile[(size_t)(r * nseg + a.nd + kp) * g.BC + cc] = cconj(x[m]);
+            }
+        }
+    }
+}
+
+/*
+ * Persistent F (grids with 2 <= X1 <= 16): grid = SMs, each CTA walks items blockIdx.x + n * gridDim.x (item =
+ * (slab, k2 batch), batch fastest). The two P boxes of item n+1 (the k2 batch and its mirror bins, NP rows x BC
+ * columns each) are fetched by tensor-map TMA while item n is transformed: round 1's F spent 63 % of its stall
+ * samples waiting for the 16 scattered P loads per thread at the top of every CTA.
+ * smem: 2 stages x 2 boxes (NP * BC complex each) | tile (R * nseg * BC complex) | 2 mbarriers.
+ */
+__global__ void __launch_bounds__(256, 1) k_chain_F_tma(NsbGeom g, ChainArgs a, const NSB_GRID_CONSTANT nsb_tmap tmP) {
+    NSB_DYN_SMEM(cd, smem_raw);
+    cd *smem = reinterpret_cast<cd *>((reinterpret_cast<size_t>(smem_raw) + 127) & ~(size_t)127);
+    const int nseg = a.nd + a.nm;
+    const int NP = a.NQ >> 1;
+    const size_t box = (size_t)NP * g.BC;
+    const size_t tw_elems = (size_t)g.BC * NSB_TWK_PITCH(g.X1);
+    cd *tile = smem + 4 * box;
+    cd *twtabs = tile + (size_t)a.R * nseg * g.BC; /* 2 stages of x twiddles (the B kernel's batch-ordered table) */
+    nsb_mbar_t *bars = reinterpret_cast<nsb_mbar_t *>(twtabs + 2 * tw_elems);
+    if (threadIdx.x == 0) {
+        nsb_mbar_init(&bars[0], 1);
+        nsb_mbar_init(&bars[1], 1);
+    }
+    __syncthreads();
+    const int nitems = a.nslab * a.nbatch;
+    auto issue = [&](int it, int st) {
+        if (threadIdx.x == 0) {
+            const int sl = (int)nsb_fastdiv((unsigned)it, a.fd_nb), kb = (it - sl * a.nbatch) * g.BC;
+            const int row0 = (a.slab0 + sl) * NP;
+            cd *dst = smem + (size_t)st * 2 * box;
+            nsb_fence_proxy_async();
+            nsb_mbar_expect_tx(&bars[st], (unsigned)(2 * box * 16) + (unsigned)(tw_elems * 16));
+            nsb_bulk_g2s(twtabs + (size_t)st * tw_elems, g.TWK + (size_t)kb * NSB_TWK_PITCH(g.X1), (unsigned)(tw_elems * 16),
+                         &bars[st]);
+            nsb_tma_2d_g2s(dst, &tmP, 2 * kb, row0, &bars[st]);
+            nsb_tma_2d_g2s(dst + box, &tmP, 2 * (1024 - kb - (g.BC - 1)), row0, &bars[st]);
+        }
+    };
+    unsigned phase[2] = {0u, 0u};
+    int item = blockIdx.x;
+    if (item < nitems) issue(item, 0);
+    for (int n = 0; item < nitems; ++n, item += gridDim.x) {
+        const int st = n & 1;
+        if (item + (int)gridDim.x < nitems) issue(item + gridDim.x, st ^ 1); /* stage st^1 was released by the barrier below */
+        nsb_mbar_wait(&bars[st], phase[st]);
+        phase[st] ^= 1u;
+        const int sl = (int)nsb_fastdiv((unsigned)item, a.fd_nb), kb = (item - sl * a.nbatch) * g.BC;
+        const cd *A = smem + (size_t)st * 2 * box, *M = A + box, *tw = twtabs + (size_t)st * tw_elems;
+        switch (g.X1) {
+            case 2: chain_F2_step1<2>(g, a, tile, A, M, tw, kb); break;
+            case 4: chain_F2_step1<4>(g, a, tile, A, M, tw, kb); break;
+            case 8: chain_F2_step1<8>(g, a, tile, A, M, tw, kb); break;
+            case 16: chain_F2_step1<16>(g, a, tile, A, M, tw, kb); break;
+            default: break;
+        }
+        __syncthreads(); /* tile complete; the boxes of this stage are free for item n+2 */
+        switch (g.Y2) {
+            case 1: chain_F_step2<1>(g, a, tile, a.slab0 + sl, kb); break;
+            case 2: chain_F_step2<2>(g, a, tile, a.slab0 + sl, kb); break;
+            case 4: chain_F_step2<4>(g, a, tile, a.slab0 + sl, kb); break;
+            case 8: chain_F_step2<8>(g, a, tile, a.slab0 + sl, kb); break;
+            case 16: chain_F_step2<16>(g, a, tile, a.slab0 + sl, kb); break;
+            default: break;
+        }
+        __syncthreads(); /* the tile is rewritten by the next item */
+    }
+}
+
 /* ------------------------------------------------ the three plain kernels */
 
 /* grid (nbatch, 2, nslab) */

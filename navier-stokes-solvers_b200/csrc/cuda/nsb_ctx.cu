@@ -102,6 +102,9 @@ struct nsb_ctx {
     int tmT_ok, tmT8_ok;
     int ch_bbc;
     int ch_gpersist;
+    int ch_ftma; /* F persistent and TMA-fed (k_chain_F_tma) */
+    nsb_tmap tmP;
+    const void *tmP_base; /* the P buffer tmP describes */
     int ch_b512; /* B with split step 2 and twice the threads (k_chain_B_tma<512, 1, false, true>) */
     int ch_g2; /* G with TMEM parking + TMA-fed inputs (k_chain_G2) */
     int ch_pieces;          /* slab ranges of the chain run on two streams (1 = one range, one stream) */
@@ -310,6 +313,8 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->ch_pieces = env_int("NSB_CHAIN_PIECES", 0);         /* 0 = automatic */
     c->ch_g2 = env_int("NSB_CHAIN_G2", 1);
     c->ch_b512 = env_int("NSB_CHAIN_B512", 1);
+    c->ch_ftma = env_int("NSB_CHAIN_FTMA", 1);
+    c->tmP_base = nullptr;
     c->ch_gpersist = env_int("NSB_CHAIN_GPERSIST", 0); /* measured: the persistent G is 6 % slower (2.93 vs 2.77 ms) */
     c->alpha_cols = env_int("NSB_ALPHA_COLS", 4) == 8 ? 8 : 4;
     c->alpha_tma = env_int("NSB_ALPHA_TMA", 1);
@@ -1193,6 +1198,19 @@ static int launch_chain(nsb_ctx *c, bool want_umax) {
                     auto k = k_chain_F<true>;
                     if (ensure_smem(c, k, tileF, true)) return -1;
                     NSB_LAUNCH(k, dim3(aF.nbatch, a.nslab), dim3(c->ch_fthreads), tileF, st, gF, aF);
+                } else if (c->ch_ftma && g.X1 >= 2 && NP <= 256 && bcF == g.BC &&
+                           4 * (size_t)NP * g.BC * sizeof(cd) + tileB / 2 + 2 * twtab + 256 <= 227 * 1024) {
+                    /* persistent, P boxes by TMA, double buffered */
+                    if (c->tmP_base != (const void *)a.P) {
+                        if (make_tmap_2d(&c->tmP, a.P, 2048, (size_t)total_slabs * NP, 1024 * sizeof(cd), 2 * g.BC, NP))
+                            return -1;
+                        c->tmP_base = (const void *)a.P;
+                    }
+                    aF.fd_nb = nsb_fastdiv_make((unsigned)aF.nbatch);
+                    const size_t smemF = 4 * (size_t)NP * g.BC * sizeof(cd) + tileB / 2 + 2 * twtab + 256;
+                    auto k = k_chain_F_tma;
+                    if (ensure_smem(c, k, smemF, true)) return -1;
+                    NSB_LAUNCH(k, dim3(c->sm_count), dim3(256), smemF, st, g, aF, c->tmP);
                 } else {
                     auto k = k_chain_F<false>;
                     if (ensure_smem(c, k, tileF, true)) return -1;
