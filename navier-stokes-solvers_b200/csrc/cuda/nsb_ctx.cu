@@ -95,6 +95,7 @@ struct nsb_ctx {
     unsigned *chCtr;   /* ticket + per-slab completion counters */
     int ch_slotZ, ch_slotP, ch_leadG, ch_leadF, ch_ctas, ch_btma;
     int alpha_cols; /* columns per CTA of the fused column kernel: 4 (two CTAs per SM) or 8 */
+    int alpha_persist; /* TMA variant: one CTA per SM walking the tiles (NSB_ALPHA_PERSIST=0: one tile per CTA) */
     int alpha_tma;  /* tile stores of the column kernel through TMA (8 columns per CTA, 128B swizzle) */
     NsbTmaps tmA;   /* tensor maps of every device's T for those stores */
     int tmA_ok;
@@ -318,6 +319,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->ch_gpersist = env_int("NSB_CHAIN_GPERSIST", 0); /* measured: the persistent G is 6 % slower (2.93 vs 2.77 ms) */
     c->alpha_cols = env_int("NSB_ALPHA_COLS", 4) == 8 ? 8 : 4;
     c->alpha_tma = env_int("NSB_ALPHA_TMA", 1);
+    c->alpha_persist = env_int("NSB_ALPHA_PERSIST", 1);
     c->tmA_ok = 0;
     if (c->ch_leadG < 1) c->ch_leadG = 1;
     if (c->ch_leadF < 1) c->ch_leadF = 1;
@@ -899,7 +901,8 @@ static int launch_alpha1024(nsb_ctx *c, bool fwd, bool inv, const AlphaFastArgs 
 #define NSB_A1024(F, I, COLS, T, SMEM)                                                          \
     {                                                                                           \
         auto k = k_alpha1024<F, I, COLS, T>;                                                    \
-        const dim3 grid((a.c1 - a.c0 + COLS - 1) / COLS, g.Y2), block(COLS * 32);               \
+        const int ntiles = ((a.c1 - a.c0 + COLS - 1) / COLS) * g.Y2;                             \
+        const dim3 grid((T) && ntiles > c->sm_count && c->alpha_persist ? c->sm_count : ntiles), block(COLS * 32); \
         if (ensure_smem(c, k, SMEM)) return -1;                                                 \
         NSB_LAUNCH(k, grid, block, SMEM, c->stream, g, a, c->tmA);                              \
     }

@@ -1065,28 +1065,55 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
     cd *TW = S + 1024 * COLS;
     cd *TB = TW + 1024; /* TB[m] = exp(-2 pi i (32 j2 m)/ny) */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j2 = blockIdx.y, ic0 = a.c0 + blockIdx.x * COLS;
-    const int ic = ic0 + warp;
-    const bool active = ic < a.c1;
     const int cc = threadIdx.x & (COLS - 1), rr = threadIdx.x / COLS; /* cooperative copies: COLS threads per row */
-    nsb_fill_tw1024(TW, g.TWY);
-    if (threadIdx.x < 32) TB[threadIdx.x] = __ldg(&g.WY[(size_t)32 * j2 * threadIdx.x]);
-    /* y twiddle exp(-2 pi i j2 y1/ny), y1 = lane + 32 m, factored as ta * TB[m] (measured: a full
-     * 1024-entry table in shared memory costs more in lost L1 than the extra complex multiply) */
-    const cd ta = __ldg(&g.WY[(size_t)j2 * lane]);
     double *KY = reinterpret_cast<double *>(TB + 32); /* ky of this CTA's rows, indexed by j1 */
     /* TMA: private 8 KB transpose buffer per warp, so the tile is not touched while its store drains */
     double *TS = KY + 1024 + (size_t)(threadIdx.x >> 5) * 1024;
-    for (int k = threadIdx.x; k < 1024; k += blockDim.x) KY[k] = __ldg(&g.kyK[(size_t)j2 * 1024 + k]);
+    nsb_mbar_t *tbar = reinterpret_cast<nsb_mbar_t *>(KY + 1024 + 8 * 1024); /* TMA only: behind the scratch */
+    const cd *Wre = FWD ? a.rk.Wst : a.Wsrc; /* state the inverse fields derive from */
+    nsb_fill_tw1024(TW, g.TWY);
+    if (TMA && threadIdx.x == 0) nsb_mbar_init(tbar, 1);
+    /*
+     * PERSISTENT over tiles (round 2): tile t = (j2, column tile), j2 slowest, CTA b takes t = b, b + gridDim.x, ...
+     * The 16 KB twiddle table is staged once per CTA, the ky / y-twiddle rows only when j2 changes, and the last
+     * TMA store of a tile drains behind the start of the next tile instead of holding the CTA at EXIT (round-2
+     * profile of the one-tile-per-CTA version: 4-11 % of the stall samples at EXIT, 3 % in the table fills).
+     * The LDG/STG variants are launched with one tile per CTA (the loop runs once).
+     */
+    const int ntx = (a.c1 - a.c0 + COLS - 1) / COLS;
+    const int ntiles = ntx * g.Y2;
+    unsigned tphase = 0u;
+    int j2_cur = -1;
+    unsigned keepmask = 0u;
+    cd ta = cmk(1.0, 0.0);
+#pragma unroll 1
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int j2 = t / ntx, ic0 = a.c0 + (t - j2 * ntx) * COLS;
+    const int ic = ic0 + warp;
+    const bool active = ic < a.c1;
+    /* the previous tile's last tile store must have READ the tile, and every warp must be done with the tile and
+     * the ky / twiddle rows, before they are refilled */
+    if (TMA && threadIdx.x == 0) nsb_tma_store_wait_read();
+    __syncthreads();
+    if (j2 != j2_cur) {
+        j2_cur = j2;
+        if (threadIdx.x < 32) TB[threadIdx.x] = __ldg(&g.WY[(size_t)32 * j2 * threadIdx.x]);
+        /* y twiddle exp(-2 pi i j2 y1/ny), y1 = lane + 32 m, factored as ta * TB[m] (measured: a full
+         * 1024-entry table in shared memory costs more in lost L1 than the extra complex multiply) */
+        ta = __ldg(&g.WY[(size_t)j2 * lane]);
+        for (int k = threadIdx.x; k < 1024; k += blockDim.x) KY[k] = __ldg(&g.kyK[(size_t)j2 * 1024 + k]);
+        /* rows of this lane that survive the 2/3 mask, one bit per register index (same for every job) */
+        keepmask = 0u;
+#pragma unroll
+        for (int m = 0; m < 32; ++m)
+            if (nsb_iabs(nsb_band((lane + 32 * m) * g.Y2 + j2, g.ny)) <= g.ycut) keepmask |= 1u << m;
+    }
     const double kxv = active ? __ldg(&g.kx[ic]) : 0.0;
     const size_t kbase = ((size_t)(ic - a.c0) * g.Y2 + j2) * 1024;
-    const cd *Wre = FWD ? a.rk.Wst : a.Wsrc; /* state the inverse fields derive from */
-    nsb_mbar_t *tbar = reinterpret_cast<nsb_mbar_t *>(KY + 1024 + 8 * 1024); /* TMA only: behind the scratch */
     if (FWD && TMA && a.tma_in) {
         /* the whole T' tile (1024 rows x 8 columns) in four tensor loads, in flight while the
-         * twiddle / ky tables above are filled by the other threads */
+         * ky / twiddle rows above are filled by the other threads */
         if (threadIdx.x == 0) {
-            nsb_mbar_init(tbar, 1);
             nsb_fence_proxy_async();
             nsb_mbar_expect_tx(tbar, 1024u * COLS * 16u);
             for (int r0 = 0; r0 < 1024; r0 += 256)
@@ -1103,14 +1130,12 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
         }
     }
     __syncthreads();
-    if (FWD && TMA && a.tma_in) nsb_mbar_wait(tbar, 0u);
+    if (FWD && TMA && a.tma_in) {
+        nsb_mbar_wait(tbar, tphase);
+        tphase ^= 1u;
+    }
     cd x[32];
     bool prefetched = false;
-    /* rows of this lane that survive the 2/3 mask, one bit per register index (same for every job) */
-    unsigned keepmask = 0u;
-#pragma unroll
-    for (int m = 0; m < 32; ++m)
-        if (nsb_iabs(nsb_band((lane + 32 * m) * g.Y2 + j2, g.ny)) <= g.ycut) keepmask |= 1u << m;
     const double kx2 = __dmul_rn(kxv, kxv);
 #pragma unroll 1
     for (int job = FWD ? 0 : 1; job <= (INV ? 4 : 0); ++job) {
@@ -1313,6 +1338,7 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
         }
         __syncthreads();
     }
+    } /* tile loop */
     if (TMA && INV && threadIdx.x == 0) nsb_tma_store_wait_read(); /* shared memory must outlive the last store */
 }
 
