@@ -676,7 +676,8 @@ __global__ void __launch_bounds__(NT, MINB) k_chain_B_tma(NsbGeom g, ChainArgs a
 /*
  * Step 1 of F on TMA-landed boxes: A[row][cc] = P[pair row][kb + cc], M[row][cc'] = P[pair row][1024 - kb - (BC-1) + cc']
  * (the mirror bins 1024 - k2 in ascending memory order, so bin 1024 - (kb + cc) sits at cc' = BC - 1 - cc), rows =
- * the NP = R * X1 / 2 comb pairs of the slab. Same arithmetic as chain_F_step1 (bit-identical results).
+ * the NP = R * X1 / 2 comb pairs of the slab. Same arithmetic as chain_F_step1 (results agree to rounding: the two
+ * kernels are contracted into FMAs differently by the compiler).
  */
 template <int X1>
 __device__ __forceinline__ void chain_F2_step1(const NsbGeom &g, const ChainArgs &a, cd *tile, const cd *A, const cd *M,
