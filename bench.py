@@ -214,7 +214,7 @@ class GpuCase:
     """One forced-turbulence solver on this rank's GPU (slab-decomposed when world > 1), driven through
     the reference-facing C entry points of lib/libns_spectral.so."""
 
-    def __init__(self, host, nsblib, n, rank, world, dist, device):
+    def __init__(self, host, nsblib, n, rank, world, dist, device, forced=True):
         import hostlib
         import ns_structs as st
         self.host, self.nsblib, self.n, self.world = host, nsblib, n, world
@@ -245,15 +245,17 @@ class GpuCase:
         host.ns_spectral_hyperviscosity_default(C.byref(h))
         h.enabled, h.coefficient, h.order, h.cutoff_ratio = 1, HV["coefficient"], HV["order"], HV["cutoff_ratio"]
         host.ns_spectral_hyperviscosity_set(s.sp, C.byref(h))
-        cfg = st.ForcingConfig()
-        host.ns_forcing_config_default(C.byref(cfg))
-        cfg.kmin, cfg.kmax, cfg.energy_target = FORCING["kmin"], FORCING["kmax"], FORCING["energy_target"]
-        cfg.correlation_time, cfg.seed, cfg.type = FORCING["tau"], FORCING["seed"], 0  # every rank replays the same stream
-        self.fs = st.ForcingState()
-        assert host.ns_forcing_state_init(C.byref(self.fs), C.byref(cfg), s.s.k2, s.s.nkx, s.s.nky) == 0
-        ib, jb = C.c_int(), C.c_int()
-        host.ns_forcing_box_extent(C.byref(self.fs), C.byref(ib), C.byref(jb))
-        self.force_bytes = (2 * jb.value + 1) * (ib.value + 1) * 16
+        self.fs, self.force_bytes = None, 0
+        if forced:
+            cfg = st.ForcingConfig()
+            host.ns_forcing_config_default(C.byref(cfg))
+            cfg.kmin, cfg.kmax, cfg.energy_target = FORCING["kmin"], FORCING["kmax"], FORCING["energy_target"]
+            cfg.correlation_time, cfg.seed, cfg.type = FORCING["tau"], FORCING["seed"], 0  # every rank replays the same stream
+            self.fs = st.ForcingState()
+            assert host.ns_forcing_state_init(C.byref(self.fs), C.byref(cfg), s.s.k2, s.s.nkx, s.s.nky) == 0
+            ib, jb = C.c_int(), C.c_int()
+            host.ns_forcing_box_extent(C.byref(self.fs), C.byref(ib), C.byref(jb))
+            self.force_bytes = (2 * jb.value + 1) * (ib.value + 1) * 16
         self.steps_taken = 0
 
     def _ck(self, rc):
@@ -261,7 +263,7 @@ class GpuCase:
             raise SystemExit("bench.py: " + self.nsblib.nsb_last_error().decode())
 
     def run(self, k):
-        assert self.host.ns_spectral_run_steps(self.s.sp, k, C.byref(self.fs)) == 0, \
+        assert self.host.ns_spectral_run_steps(self.s.sp, k, C.byref(self.fs) if self.fs is not None else None) == 0, \
             self.host.ns_spectral_last_error()
         self.steps_taken += k
 
@@ -299,7 +301,8 @@ class GpuCase:
         return {"Y1": plan[0], "Y2": plan[1], "X1": plan[2], "X2": plan[3]}
 
     def close(self):
-        self.host.ns_forcing_state_free(C.byref(self.fs))
+        if self.fs is not None:
+            self.host.ns_forcing_state_free(C.byref(self.fs))
         self.s.close()
 
 
@@ -332,7 +335,8 @@ def run_gpu_arm(args):
     os.environ["NS_SPECTRAL_DEVICE"] = str(device)
     peak, peak_src = measured_peaks()
 
-    g = GpuCase(host, nsblib, n, rank, world, dist, device)
+    forced = args.workload == "forced"
+    g = GpuCase(host, nsblib, n, rank, world, dist, device, forced=forced)
     g.run(args.warmup)
 
     # ---- device-resident timed region: exactly K steps
@@ -481,9 +485,12 @@ def run_gpu_arm(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"forced 2-D turbulence {n}x{n} FP64, hyperviscosity + white forcing, adaptive CFL "
-                                   f"dt (BASELINE config {'4' if n == 16384 else '3' if n == 4096 else '5 grid, forced' if n == 32768 else 'n=' + str(n)})",
-                       "Re": RE, "hyperviscosity": HV, "forcing": {"type": "white", **FORCING},
+            "config": {"workload": (f"forced 2-D turbulence {n}x{n} FP64, hyperviscosity + white forcing, adaptive CFL "
+                                    f"dt (BASELINE config {'4' if n == 16384 else '3' if n == 4096 else '5 grid, forced' if n == 32768 else 'n=' + str(n)})")
+                       if forced else
+                       (f"decaying 2-D turbulence {n}x{n} FP64, hyperviscosity, no forcing, adaptive CFL dt (BASELINE config "
+                        f"{'5' if n == 32768 else '2' if n == 1024 else 'n=' + str(n)})"),
+                       "Re": RE, "hyperviscosity": HV, "forcing": {"type": "white", **FORCING} if forced else {"type": "none"},
                        "init": "ns_spectral_initialize_random_phase: spectrum k^2 exp(-(k/8)^2), splitmix64 phases "
                                "(seed 7), max|omega| = 5 (SURVEY 8d)",
                        "parallelism": "1 GPU" if world == 1 else
@@ -509,6 +516,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3, help="timed CPU steps (0 = skip cpu_baseline)")
     ap.add_argument("--eager-steps", type=int, default=1, help="strict EAGER drop-in steps (0 = skip)")
     ap.add_argument("--secondary-n", type=int, default=4096, help="grid of the secondary result (0 = skip)")
+    ap.add_argument("--workload", default="forced", choices=["forced", "decaying"],
+                    help="forced: BASELINE configs 3/4 (white forcing); decaying: configs 2/5 (no forcing)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

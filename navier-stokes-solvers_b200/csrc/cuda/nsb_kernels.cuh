@@ -1086,6 +1086,8 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
     int j2_cur = -1;
     unsigned keepmask = 0u;
     cd ta = cmk(1.0, 0.0);
+    cd x[32];
+    bool prefetched = false; /* x already holds the input of the next inverse job */
 #pragma unroll 1
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int j2 = t / ntx, ic0 = a.c0 + (t - j2 * ntx) * COLS;
@@ -1134,8 +1136,6 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
         nsb_mbar_wait(tbar, tphase);
         tphase ^= 1u;
     }
-    cd x[32];
-    bool prefetched = false;
     const double kx2 = __dmul_rn(kxv, kxv);
 #pragma unroll 1
     for (int job = FWD ? 0 : 1; job <= (INV ? 4 : 0); ++job) {
@@ -1307,6 +1307,21 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
 #pragma unroll
                 for (int m = 0; m < 32; ++m) x[m] = Wre[kbase + lane + 32 * m];
                 prefetched = true;
+            }
+        }
+        if (!FWD && job == 4) {
+            /* inverse-only launch (stage 1): the first input of the NEXT tile of this CTA, so that its 32 loads per
+             * lane are in flight behind this tile's last store instead of stalling the next tile's first transform */
+            prefetched = false;
+            const int tn = t + (int)gridDim.x;
+            if (tn < ntiles) {
+                const int j2n = tn / ntx, icn = a.c0 + (tn - j2n * ntx) * COLS + warp;
+                if (icn < a.c1) {
+                    const size_t kbn = ((size_t)(icn - a.c0) * g.Y2 + j2n) * 1024;
+#pragma unroll
+                    for (int m = 0; m < 32; ++m) x[m] = Wre[kbn + lane + 32 * m];
+                    prefetched = true;
+                }
             }
         }
         if (TMA) nsb_fence_proxy_async(); /* generic-proxy tile writes -> visible to the TMA store */
