@@ -139,6 +139,10 @@ int nsb_rk4_step_finish(nsb_ctx **ctxs, int n);
 int nsb_diagnostics(nsb_ctx *c, double out[4]);
 /* same sums from the device copies of the physical arrays U, V, OMEGA */
 int nsb_diagnostics_phys(nsb_ctx *c, double out[4]);
+/* out[0..2] as nsb_diagnostics, by Parseval over the retained modes (Hermitian projection of the kx = 0 column, as
+ * the c2r of spectral_transforms.c:25-32 applies it) instead of three c2r transforms; on a context of a
+ * slab-decomposed group over the own columns only: add the results of all devices. Synchronous. */
+int nsb_diagnostics_spectral(nsb_ctx *c, double out[3]);
 
 /* The reductions over OMEGA_HAT that ns_spectral_check_resolution (spectral_analysis.c:36-66) and
  * ns_spectral_analyze_convergence (:69-100) make, on the device: out = { sum |w|^2, sum |w|^2 over

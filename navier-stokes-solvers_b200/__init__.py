@@ -100,6 +100,7 @@ def load_nsb(path=None):
         "nsb_energy_spectrum": [C.c_void_p, C.c_int, c_double_p, C.POINTER(C.c_int)],
         "nsb_mgpu_group_gather": [C.POINTER(C.c_void_p), C.c_int],
         "nsb_state_checksum": [C.c_void_p, C.POINTER(C.c_ulonglong)],
+        "nsb_diagnostics_spectral": [C.c_void_p, c_double_p],
         "nsb_mgpu_group_scatter": [C.POINTER(C.c_void_p), C.c_int],
     }
     for name, args in sigs.items():
@@ -234,6 +235,13 @@ class NsbContext:
         n = float(self.nx * self.ny)
         return {"energy": 0.5 * (out[0] + out[1]) / n, "enstrophy": 0.5 * out[2] / n,
                 "max_speed": float(np.sqrt(out[3]))}
+
+    def diagnostics_spectral(self):
+        """energy / enstrophy by Parseval over the retained modes (no transforms)"""
+        out = (C.c_double * 3)()
+        self._ck(self.lib.nsb_diagnostics_spectral(self.h, out))
+        n = float(self.nx * self.ny)
+        return {"energy": 0.5 * (out[0] + out[1]) / n, "enstrophy": 0.5 * out[2] / n}
 
     def spectral_stats(self):
         out = (C.c_double * 6)()

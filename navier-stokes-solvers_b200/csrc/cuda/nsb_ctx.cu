@@ -2227,6 +2227,72 @@ extern "C" int nsb_mgpu_group_scatter(nsb_ctx **cs, int n) {
     return 0;
 }
 
+/* ---------------------------------------------------- energy / enstrophy by Parseval (device groups) */
+
+static void reduction_columns(const nsb_ctx *c, int *ca, int *cb);
+
+/* sum over the grid of u^2, v^2, omega^2 (ns_spectral_compute_energy / _enstrophy, spectral_analysis.c:8-33) WITHOUT
+ * the three c2r transforms, from the modes of columns [ca, cb): mean(f^2) = sum_j |P f_hat(0, j)|^2 +
+ * 2 sum_{i>=1} sum_j |f_hat(i, j)|^2 over the modes the 2/3 mask keeps, where P is the Hermitian projection
+ * (f(j) + conj f(-j)) / 2 of the kx = 0 column -- the c2r of spectral_transforms.c:25-32 drops the imaginary part of
+ * that column after the y pass, so a non-Hermitian kx = 0 column (the forcing draws one) contributes only its
+ * projection. u_hat = i ky psi_hat, v_hat = -i kx psi_hat, psi_hat = -omega_hat / k^2 (spectral_core.c:17-31).
+ * acc[0..2] += N * (the three means). Partial sums of the devices of a slab-decomposed group add up. */
+__global__ void __launch_bounds__(256) k_parseval_sums(NsbGeom g, const cd *W, int ca, int cb, double *acc) {
+    NSB_DYN_SMEM(double, red);
+    const int w = cb - ca;
+    const size_t total = (size_t)w * g.ny;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(k / w), i = ca + (int)(k - (size_t)j * w);
+        if (i > g.imax || nsb_iabs(nsb_band(j, g.ny)) > g.ycut) continue;
+        const double kxv = g.kx[i], kyv = g.ky[j];
+        const double k2 = __dadd_rn(__dmul_rn(kxv, kxv), __dmul_rn(kyv, kyv));
+        cd om = W[(size_t)j * g.nkx + i];
+        cd uh = nsb_ik(kyv, nsb_psi_from_w(om, k2));
+        cd vh = nsb_ik(kxv, nsb_psi_from_w(om, k2));
+        double wt = 2.0;
+        if (i == 0) {
+            const int jm = (g.ny - j) % g.ny;
+            const cd omm = W[(size_t)jm * g.nkx];
+            const cd uhm = nsb_ik(g.ky[jm], nsb_psi_from_w(omm, k2));
+            om = cmk(0.5 * (om.x + omm.x), 0.5 * (om.y - omm.y));
+            uh = cmk(0.5 * (uh.x + uhm.x), 0.5 * (uh.y - uhm.y));
+            vh = cmk(0.0, 0.0);
+            wt = 1.0;
+        }
+        s[0] += wt * (uh.x * uh.x + uh.y * uh.y);
+        s[1] += wt * (vh.x * vh.x + vh.y * vh.y);
+        s[2] += wt * (om.x * om.x + om.y * om.y);
+    }
+    const double n = (double)g.nx * (double)g.ny;
+    nsb_block_sum_to_global(s[0] * n, acc + 0, red);
+    nsb_block_sum_to_global(s[1] * n, acc + 1, red);
+    nsb_block_sum_to_global(s[2] * n, acc + 2, red);
+}
+
+extern "C" int nsb_diagnostics_spectral(nsb_ctx *c, double out[3]) {
+    if (!c || !out) return fail("nsb_diagnostics_spectral: null argument");
+    CK(cudaSetDevice(c->device));
+    if (sync_ref(c)) return -1;
+    void *w;
+    if (get_field(c, NSB_OMEGA_HAT, &w)) return -1;
+    CK(cudaMemsetAsync(c->d_sc->sums, 0, sizeof(double) * 4, c->stream));
+    int ca, cb;
+    reduction_columns(c, &ca, &cb);
+    if (cb > c->g.ncol) cb = c->g.ncol; /* masked columns contribute nothing */
+    if (cb > ca) {
+        auto k = k_parseval_sums;
+        NSB_LAUNCH(k, dim3(pointwise_grid(c)), dim3(256), 256 * sizeof(double), c->stream, c->g, (const cd *)w, ca, cb,
+                   c->d_sc->sums);
+        CKL();
+        c->launches++;
+    }
+    if (fetch_scalars(c)) return -1;
+    out[0] = c->h_sc->sums[0]; out[1] = c->h_sc->sums[1]; out[2] = c->h_sc->sums[2];
+    return 0;
+}
+
 /* ---------------------------------------------------- state fingerprint */
 
 __global__ void __launch_bounds__(256) k_state_checksum(NsbGeom g, const cd *W, int c0, int c1, unsigned long long *out) {

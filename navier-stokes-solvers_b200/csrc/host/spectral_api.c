@@ -598,7 +598,19 @@ int ns_spectral_run_steps(NSSpectralData *d, int n, NSForcingState *fs) {
 
 /* ------------------------------------------------------------- diagnostics */
 
+static int group_partial(const NSSpectralData *d);
+
 static void sums(NSSpectralData *d, double out[4], const char *where) {
+    if (group_partial(d)) { /* Parseval partial sums over every device's own columns, no gather */
+        Backend *b = backend_of(d);
+        out[0] = out[1] = out[2] = out[3] = 0.0;
+        for (int r = 0; r < b->ngpus; ++r) {
+            double part[3];
+            NSB_OK(nsb_diagnostics_spectral(b->group[r], part), where);
+            out[0] += part[0]; out[1] += part[1]; out[2] += part[2];
+        }
+        return;
+    }
     nsb_ctx *c = ctx_ro(d, where);
     if (lazy(d)) {
         NSB_OK(nsb_diagnostics(c, out), where);
@@ -698,7 +710,7 @@ int ns_spectral_check_resolution(NSSpectralData *d) {
 void ns_spectral_analyze_convergence(NSSpectralData *d, int step) {
     static const char *W = "ns_spectral_analyze_convergence";
     if (step % 10 != 0) return;
-    ctx_ro(d, W);
+    if (!group_partial(d)) ctx_ro(d, W);
     double s[4];
     sums(d, s, W);
     const double energy = 0.5 * (s[0] + s[1]) / (d->nx * d->ny);

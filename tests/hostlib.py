@@ -73,7 +73,7 @@ NSB_SYMBOLS = [
     "nsb_mgpu_setup", "nsb_mgpu_partition", "nsb_mgpu_export", "nsb_mgpu_import", "nsb_mgpu_link_local",
     "nsb_mgpu_group_step", "nsb_mgpu_group_gather", "nsb_mgpu_group_scatter", "nsb_spectral_stats",
     "nsb_energy_spectrum", "nsb_state_checksum", "nsb_phys_absmax", "nsb_phys_scale", "nsb_set_physics", "nsb_velocity_statistics",
-    "nsb_velocity_statistics_host", "nsb_check_finite", "nsb_download_columns", "nsb_rk4_step_begin", "nsb_rk4_step_finish",
+    "nsb_velocity_statistics_host", "nsb_check_finite", "nsb_download_columns", "nsb_rk4_step_begin", "nsb_rk4_step_finish", "nsb_diagnostics_spectral",
 ]
 
 

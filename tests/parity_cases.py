@@ -157,3 +157,17 @@ def check_spectral_stats(nsb, lib, nx, ny, **plan):
     want = np.bincount(bins[ok], weights=e[ok], minlength=nb)
     assert np.max(np.abs(ek - want)) <= 1e-12 * want.max()
     c.close()
+
+
+def check_parseval(nsb, lib, nx, ny, **plan):
+    """nsb_diagnostics_spectral (Parseval over the retained modes, Hermitian projection of the kx = 0 column) against
+    nsb_diagnostics (three c2r transforms + sums over the grid, spectral_analysis.c:8-33) on a GENERAL omega_hat:
+    non-Hermitian kx = 0 column, non-zero masked modes."""
+    rng = np.random.default_rng(23)
+    c = nsb.NsbContext(nx, ny, lib=lib, **plan)
+    w = rng.standard_normal((ny, nx // 2 + 1)) + 1j * rng.standard_normal((ny, nx // 2 + 1))
+    c.upload(nsb.OMEGA_HAT, w)
+    a, b = c.diagnostics(), c.diagnostics_spectral()
+    assert abs(a["energy"] - b["energy"]) <= 1e-13 * a["energy"], (a, b)
+    assert abs(a["enstrophy"] - b["enstrophy"]) <= 1e-13 * a["enstrophy"], (a, b)
+    c.close()

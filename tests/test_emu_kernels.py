@@ -181,3 +181,8 @@ def test_emu_slab_decomposition_two_devices(nsb, emu_lib):
 
 def test_emu_spectral_stats(nsb, emu_lib):
     pc.check_spectral_stats(nsb, emu_lib, 64, 32)
+
+
+def test_emu_parseval_diagnostics(nsb, emu_lib):
+    pc.check_parseval(nsb, emu_lib, 64, 32)
+    pc.check_parseval(nsb, emu_lib, 32, 64, y1=8, x2=8)

@@ -381,6 +381,11 @@ def test_host_backend_init_device_group(monkeypatch):
             assert abs(a - b) <= 1e-13 * abs(b)
 
 
+def test_parseval_diagnostics(nsb, cuda_lib):
+    pc.check_parseval(nsb, cuda_lib, 512, 256)
+    pc.check_parseval(nsb, cuda_lib, 2048, 2048)
+
+
 def test_spectral_stats(nsb, cuda_lib):
     """device-side reductions of the driver-loop diagnostics (no field download in LAZY mode)"""
     pc.check_spectral_stats(nsb, cuda_lib, 512, 256)
