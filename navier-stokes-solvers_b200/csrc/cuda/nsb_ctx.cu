@@ -95,6 +95,7 @@ struct nsb_ctx {
     unsigned *chCtr;   /* ticket + per-slab completion counters */
     int ch_slotZ, ch_slotP, ch_leadG, ch_leadF, ch_ctas, ch_btma;
     int alpha_cols; /* columns per CTA of the fused column kernel: 4 (two CTAs per SM) or 8 */
+    int alpha_groups;  /* TMA variant: 1 = eight columns per CTA, 2 = two independent 4-column groups per CTA */
     int alpha_persist; /* TMA variant: one CTA per SM walking the tiles (NSB_ALPHA_PERSIST=0: one tile per CTA) */
     int alpha_tma;  /* tile stores of the column kernel through TMA (8 columns per CTA, 128B swizzle) */
     NsbTmaps tmA;   /* tensor maps of every device's T for those stores */
@@ -320,6 +321,7 @@ extern "C" int nsb_ctx_create(const nsb_params *p, nsb_ctx **out) {
     c->alpha_cols = env_int("NSB_ALPHA_COLS", 4) == 8 ? 8 : 4;
     c->alpha_tma = env_int("NSB_ALPHA_TMA", 1);
     c->alpha_persist = env_int("NSB_ALPHA_PERSIST", 1);
+    c->alpha_groups = env_int("NSB_ALPHA_GROUPS", 0); /* 0 = automatic: 2 on one device, 1 when slab-decomposed */
     c->tmA_ok = 0;
     if (c->ch_leadG < 1) c->ch_leadG = 1;
     if (c->ch_leadF < 1) c->ch_leadF = 1;
@@ -838,11 +840,12 @@ static int launch_beta(nsb_ctx *c, bool inverse, const BetaArgs &a) {
  * 128-byte swizzle (box0 must be 16 doubles): the tile stores of k_alpha1024<.., TMA> */
 static int make_tmap_3d_sw128(nsb_tmap *out, const void *base, size_t dim0, size_t dim1, size_t dim2, size_t s1,
                               size_t s2, int box0, int box2) {
+    /* box0 == 16 doubles: 128-byte rows, SWIZZLE_128B; box0 == 8 doubles: 64-byte rows, SWIZZLE_64B */
 #ifdef NSB_EMULATE
     out->base = (const double *)base;
     out->dim0 = (long long)dim0; out->dim1 = (long long)dim1; out->dim2 = (long long)dim2;
     out->stride1 = (long long)s1; out->stride2 = (long long)s2;
-    out->box0 = box0; out->box1 = 1; out->box2 = box2; out->swz = 1;
+    out->box0 = box0; out->box1 = 1; out->box2 = box2; out->swz = box0 == 8 ? 2 : 1;
     return 0;
 #else
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -857,7 +860,8 @@ static int make_tmap_3d_sw128(nsb_tmap *out, const void *base, size_t dim0, size
     const cuuint32_t box[3] = {(cuuint32_t)box0, 1u, (cuuint32_t)box2};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = ((encode_fn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), gdim, gstr, box,
-                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       box0 == 8 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
     return 0;
@@ -887,12 +891,19 @@ static int launch_alpha1024(nsb_ctx *c, bool fwd, bool inv, const AlphaFastArgs 
         a.tma_in = (fwd && c->bufTp && a.in == c->bufTp && a.in_pitch == c->mg_cb) ? 1 : 0;
         a.tma_br = a.tma_rl < 256 ? a.tma_rl : 256;
         if (!c->tmA_ok) {
-            for (int p = 0; p < c->mg_world; ++p)
+            for (int p = 0; p < c->mg_world; ++p) {
                 if (make_tmap_3d_sw128(&c->tmA.m[p], c->mg_T[p], (size_t)2 * g.PT, (size_t)g.Y2, (size_t)4 * a.tma_rl,
                                        (size_t)g.PT * sizeof(cd), (size_t)g.Y2 * g.PT * sizeof(cd), 16, a.tma_br))
                     return -1;
+                if (make_tmap_3d_sw128(&c->tmA.m4[p], c->mg_T[p], (size_t)2 * g.PT, (size_t)g.Y2, (size_t)4 * a.tma_rl,
+                                       (size_t)g.PT * sizeof(cd), (size_t)g.Y2 * g.PT * sizeof(cd), 8, a.tma_br))
+                    return -1;
+            }
             if (c->bufTp && make_tmap_3d_sw128(&c->tmA.tp, c->bufTp, (size_t)2 * c->mg_cb, (size_t)g.Y2, (size_t)g.Y1,
                                                (size_t)c->mg_cb * sizeof(cd), (size_t)g.Y2 * c->mg_cb * sizeof(cd), 16, 256))
+                return -1;
+            if (c->bufTp && make_tmap_3d_sw128(&c->tmA.tp4, c->bufTp, (size_t)2 * c->mg_cb, (size_t)g.Y2, (size_t)g.Y1,
+                                               (size_t)c->mg_cb * sizeof(cd), (size_t)g.Y2 * c->mg_cb * sizeof(cd), 8, 256))
                 return -1;
             c->tmA_ok = 1;
         }
@@ -910,7 +921,24 @@ static int launch_alpha1024(nsb_ctx *c, bool fwd, bool inv, const AlphaFastArgs 
         if (ensure_smem(c, k, SMEM)) return -1;                                                 \
         NSB_LAUNCH(k, grid, block, SMEM, c->stream, g, a, c->tmA);                              \
     }
-    if (tma) {
+    if (tma && (c->alpha_groups == 2 || (c->alpha_groups == 0 && c->mg_world == 1))) {
+        /* two independent 4-column groups per CTA: two tiles in flight per SM (measured at 16384^2: 3.95 -> 3.86 ms
+         * per fused launch, 2.96 -> 2.76 ms for the stage-1 launch). Slab-decomposed runs keep the 8-column tiles:
+         * their 128-byte peer stores beat 64-byte ones by a quarter on NVLink (round 1). */
+#define NSB_A1024_2G(F, I)                                                                      \
+    {                                                                                           \
+        auto k = k_alpha1024<F, I, 4, true, 2>;                                                 \
+        const int ntiles = ((a.c1 - a.c0 + 3) / 4) * g.Y2;                                      \
+        const bool persist = 2 * c->sm_count < ntiles && c->alpha_persist && (c->mg_world == 1 || c->alpha_persist > 1); \
+        const dim3 grid(persist ? c->sm_count : (ntiles + 1) / 2), block(256);                  \
+        if (ensure_smem(c, k, NSB_A1024_SMEM_2G)) return -1;                                    \
+        NSB_LAUNCH(k, grid, block, NSB_A1024_SMEM_2G, c->stream, g, a, c->tmA);                 \
+    }
+        if (fwd && inv) NSB_A1024_2G(true, true)
+        else if (fwd) NSB_A1024_2G(true, false)
+        else NSB_A1024_2G(false, true)
+#undef NSB_A1024_2G
+    } else if (tma) {
         if (fwd && inv) NSB_A1024(true, true, 8, true, NSB_A1024_SMEM_TMA)
         else if (fwd) NSB_A1024(true, false, 8, true, NSB_A1024_SMEM_TMA)
         else NSB_A1024(false, true, 8, true, NSB_A1024_SMEM_TMA)

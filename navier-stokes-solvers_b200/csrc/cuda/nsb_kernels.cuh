@@ -984,6 +984,7 @@ struct AlphaFastArgs {
 struct NsbTmaps {
     nsb_tmap m[NSB_MAXP];
     nsb_tmap tp; /* the local T' buffer: {2*cb doubles, Y2, Y1}, for the TMA load of the forward tile */
+    nsb_tmap m4[NSB_MAXP], tp4; /* the same with 4-column boxes and the 64-byte swizzle (two-group column kernel) */
 };
 
 /* modes per lane whose RK state loads are in flight together in the in-register RK update of
@@ -1004,6 +1005,8 @@ struct NsbTmaps {
 #define NSB_A1024_COLS 4 /* granularity of the column partition; kernels take 4 or 8 columns per CTA */
 #define NSB_A1024_SMEM(COLS) (1024 * 16 + 1024 * (COLS) * 16 + 32 * 16 + 1024 * 8)
 #define NSB_A1024_SMEM_TMA (NSB_A1024_SMEM(8) + 8 * 8192 + 16 + 1024)
+/* two groups: 2 x 64 KB tiles | 16 KB FFT twiddles | 2 x (TB 512 B + KY 8 KB) | 8 x 8 KB transpose buffers | 2 mbarriers */
+#define NSB_A1024_SMEM_2G (2 * 1024 * 4 * 16 + 1024 * 16 + 2 * (32 * 16 + 1024 * 8) + 8 * 8192 + 16 + 1024)
 
 /* shared tile S[1024 rows][4 columns], 16-byte chunks XOR-swizzled so that row-wise
  * (cooperative, coalesced) and column-wise (per-warp FFT) accesses are both conflict free */
@@ -1055,24 +1058,37 @@ __device__ NSB_NOINLINE cd nsb_rk_update_call(const NsbRk *r, size_t idx, double
  *                y twiddle -> tile -> cooperative coalesced store to T[f]
  * Replaces k_alpha_fwd<RK> of stage s followed by k_alpha_inv<STEP> of stage s+1.
  */
-template <bool FWD, bool INV, int COLS, bool TMA>
-__global__ void __launch_bounds__(COLS * 32, 8 / COLS)
+template <bool FWD, bool INV, int COLS, bool TMA, int GROUPS = 1>
+__global__ void __launch_bounds__(COLS * 32 * GROUPS, 8 / (COLS * GROUPS))
     k_alpha1024(NsbGeom g, AlphaFastArgs a, const NSB_GRID_CONSTANT NsbTmaps tm) {
+    /* GROUPS == 2 (TMA, COLS == 4): the CTA is two independent 4-warp groups, each with its own 64 KB tile, ky /
+     * twiddle rows, mbarrier and tile sequence, synchronising on its own named barrier -- two tiles in flight per SM,
+     * so that one group's T' load, RK update and store drain overlap the other's transforms. Only the 16 KB
+     * FFT twiddle table is shared. (gt = thread index within the group.) */
+    const int gi = GROUPS > 1 ? (int)(threadIdx.x / (COLS * 32)) : 0;
+    const int gt = GROUPS > 1 ? (int)(threadIdx.x % (COLS * 32)) : (int)threadIdx.x;
+#define NSB_GSYNC()                                         \
+    do {                                                    \
+        if (GROUPS > 1) nsb_group_barrier(1 + gi, COLS * 32); \
+        else __syncthreads();                               \
+    } while (0)
     NSB_DYN_SMEM(cd, smem_raw);
     /* TMA: the tile must start on a 1024-byte boundary so that nsb_sidx<8> IS the 128B swizzle */
     cd *smem = TMA ? smem_raw + nsb_smem_align_pad(smem_raw, 1024) / sizeof(cd) : smem_raw;
-    cd *S = smem;
-    cd *TW = S + 1024 * COLS;
-    cd *TB = TW + 1024; /* TB[m] = exp(-2 pi i (32 j2 m)/ny) */
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cc = threadIdx.x & (COLS - 1), rr = threadIdx.x / COLS; /* cooperative copies: COLS threads per row */
-    double *KY = reinterpret_cast<double *>(TB + 32); /* ky of this CTA's rows, indexed by j1 */
+    cd *S = smem + (size_t)gi * 1024 * COLS;
+    cd *TW = smem + (size_t)GROUPS * 1024 * COLS;
+    cd *TB = TW + 1024 + (size_t)gi * 32; /* TB[m] = exp(-2 pi i (32 j2 m)/ny) */
+    const int lane = threadIdx.x & 31, warp = gt >> 5; /* warp = column of the group's tile */
+    const int cc = gt & (COLS - 1), rr = gt / COLS; /* cooperative copies: COLS threads per row */
+    double *KY = reinterpret_cast<double *>(TW + 1024 + GROUPS * 32) + (size_t)gi * 1024; /* ky of the tile's rows, by j1 */
     /* TMA: private 8 KB transpose buffer per warp, so the tile is not touched while its store drains */
-    double *TS = KY + 1024 + (size_t)(threadIdx.x >> 5) * 1024;
-    nsb_mbar_t *tbar = reinterpret_cast<nsb_mbar_t *>(KY + 1024 + 8 * 1024); /* TMA only: behind the scratch */
+    double *TS = reinterpret_cast<double *>(TW + 1024 + GROUPS * 32) + (size_t)GROUPS * 1024 + (size_t)(threadIdx.x >> 5) * 1024;
+    nsb_mbar_t *tbar = reinterpret_cast<nsb_mbar_t *>(reinterpret_cast<double *>(TW + 1024 + GROUPS * 32) +
+                                                      (size_t)GROUPS * 1024 + 8 * 1024) + gi; /* TMA only */
     const cd *Wre = FWD ? a.rk.Wst : a.Wsrc; /* state the inverse fields derive from */
     nsb_fill_tw1024(TW, g.TWY);
-    if (TMA && threadIdx.x == 0) nsb_mbar_init(tbar, 1);
+    if (TMA && gt == 0) nsb_mbar_init(tbar, 1);
+    if (GROUPS > 1) __syncthreads(); /* the shared twiddle table; from here on the groups only meet themselves */
     /*
      * PERSISTENT over tiles (round 2): tile t = (j2, column tile), j2 slowest, CTA b takes t = b, b + gridDim.x, ...
      * The 16 KB twiddle table is staged once per CTA, the ky / y-twiddle rows only when j2 changes, and the last
@@ -1089,21 +1105,21 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
     cd x[32];
     bool prefetched = false; /* x already holds the input of the next inverse job */
 #pragma unroll 1
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (int t = GROUPS * (int)blockIdx.x + gi; t < ntiles; t += GROUPS * (int)gridDim.x) {
     const int j2 = t / ntx, ic0 = a.c0 + (t - j2 * ntx) * COLS;
     const int ic = ic0 + warp;
     const bool active = ic < a.c1;
     /* the previous tile's last tile store must have READ the tile, and every warp must be done with the tile and
      * the ky / twiddle rows, before they are refilled */
-    if (TMA && threadIdx.x == 0) nsb_tma_store_wait_read();
-    __syncthreads();
+    if (TMA && gt == 0) nsb_tma_store_wait_read();
+    NSB_GSYNC();
     if (j2 != j2_cur) {
         j2_cur = j2;
-        if (threadIdx.x < 32) TB[threadIdx.x] = __ldg(&g.WY[(size_t)32 * j2 * threadIdx.x]);
+        if (gt < 32) TB[gt] = __ldg(&g.WY[(size_t)32 * j2 * gt]);
         /* y twiddle exp(-2 pi i j2 y1/ny), y1 = lane + 32 m, factored as ta * TB[m] (measured: a full
          * 1024-entry table in shared memory costs more in lost L1 than the extra complex multiply) */
         ta = __ldg(&g.WY[(size_t)j2 * lane]);
-        for (int k = threadIdx.x; k < 1024; k += blockDim.x) KY[k] = __ldg(&g.kyK[(size_t)j2 * 1024 + k]);
+        for (int k = gt; k < 1024; k += COLS * 32) KY[k] = __ldg(&g.kyK[(size_t)j2 * 1024 + k]);
         /* rows of this lane that survive the 2/3 mask, one bit per register index (same for every job) */
         keepmask = 0u;
 #pragma unroll
@@ -1115,11 +1131,11 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
     if (FWD && TMA && a.tma_in) {
         /* the whole T' tile (1024 rows x 8 columns) in four tensor loads, in flight while the
          * ky / twiddle rows above are filled by the other threads */
-        if (threadIdx.x == 0) {
+        if (gt == 0) {
             nsb_fence_proxy_async();
             nsb_mbar_expect_tx(tbar, 1024u * COLS * 16u);
             for (int r0 = 0; r0 < 1024; r0 += 256)
-                nsb_tma_3d_g2s(S + (size_t)r0 * COLS, &tm.tp, 2 * (ic0 - a.c0), j2, r0, tbar);
+                nsb_tma_3d_g2s(S + (size_t)r0 * COLS, COLS == 4 ? &tm.tp4 : &tm.tp, 2 * (ic0 - a.c0), j2, r0, tbar);
         }
     } else if (FWD) {
         const bool colok = ic0 + cc < a.c1;
@@ -1131,7 +1147,7 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
             S[nsb_sidx<COLS>(row, cc)] = v;
         }
     }
-    __syncthreads();
+    NSB_GSYNC();
     if (FWD && TMA && a.tma_in) {
         nsb_mbar_wait(tbar, tphase);
         tphase ^= 1u;
@@ -1291,8 +1307,8 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
         if (TMA && job >= 2) {
             /* the tile store of the previous job ran behind this transform; it must have finished
              * READING the tile before the tile is overwritten */
-            if (threadIdx.x == 0) nsb_tma_store_wait_read();
-            __syncthreads();
+            if (gt == 0) nsb_tma_store_wait_read();
+            NSB_GSYNC();
         }
         if (active) {
 #pragma unroll
@@ -1313,7 +1329,7 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
             /* inverse-only launch (stage 1): the first input of the NEXT tile of this CTA, so that its 32 loads per
              * lane are in flight behind this tile's last store instead of stalling the next tile's first transform */
             prefetched = false;
-            const int tn = t + (int)gridDim.x;
+            const int tn = t + GROUPS * (int)gridDim.x;
             if (tn < ntiles) {
                 const int j2n = tn / ntx, icn = a.c0 + (tn - j2n * ntx) * COLS + warp;
                 if (icn < a.c1) {
@@ -1325,14 +1341,14 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
             }
         }
         if (TMA) nsb_fence_proxy_async(); /* generic-proxy tile writes -> visible to the TMA store */
-        __syncthreads();
+        NSB_GSYNC();
         if (TMA) {
-            /* one thread hands the whole tile to the TMA unit: 1024 / tma_br boxes of tma_br rows x 8
+            /* one thread hands the whole tile to the TMA unit: 1024 / tma_br boxes of tma_br rows x COLS
              * columns, each to the device that owns those rows; no barrier, the next transform starts */
-            if (threadIdx.x == 0) {
+            if (gt == 0) {
                 for (int r0 = 0; r0 < 1024; r0 += a.tma_br) {
                     const int owner = r0 / a.tma_rl;
-                    nsb_tma_3d_s2g(&tm.m[owner], S + (size_t)r0 * COLS, 2 * ic0, j2,
+                    nsb_tma_3d_s2g(COLS == 4 ? &tm.m4[owner] : &tm.m[owner], S + (size_t)r0 * COLS, 2 * ic0, j2,
                                    (job - 1) * a.tma_rl + (r0 - owner * a.tma_rl));
                 }
                 nsb_tma_store_commit();
@@ -1351,10 +1367,11 @@ __global__ void __launch_bounds__(COLS * 32, 8 / COLS)
                 }
             }
         }
-        __syncthreads();
+        NSB_GSYNC();
     }
     } /* tile loop */
-    if (TMA && INV && threadIdx.x == 0) nsb_tma_store_wait_read(); /* shared memory must outlive the last store */
+    if (TMA && INV && gt == 0) nsb_tma_store_wait_read(); /* shared memory must outlive the last store */
+#undef NSB_GSYNC
 }
 
 #endif

@@ -74,6 +74,16 @@ __device__ __forceinline__ unsigned nsb_fastdiv(unsigned n, NsbFastDiv f) { retu
 __device__ __forceinline__ int nsb_log2i(int v) { return 31 - __clz(v); }
 #endif
 
+/* barrier among the `nthreads` consecutive threads of group `id - 1` of the CTA (bar.sync id, nthreads): the two
+ * independent 4-warp halves of the two-group column kernel synchronise separately */
+#ifdef NSB_EMULATE
+static inline void nsb_group_barrier(int id, int nthreads) { nsbemu::named_barrier(id, nthreads); }
+#else
+__device__ __forceinline__ void nsb_group_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+#endif
+
 /* correctly rounded FP64 reciprocal (MUFU.RCP64H + Newton, inlined: no division subroutine) */
 #ifdef NSB_EMULATE
 static inline double nsb_drcp(double a) { return 1.0 / a; }
@@ -186,7 +196,7 @@ static inline void nsb_tma_3d_s2g(const nsb_tmap *m, const void *src, int c0, in
         for (int e = 0; e < m->box0; ++e) {
             const long long i2 = (long long)c2 + r, i1 = c1, i0 = (long long)c0 + e;
             if (i2 < 0 || i2 >= m->dim2 || i1 < 0 || i1 >= m->dim1 || i0 < 0 || i0 >= m->dim0) continue;
-            const size_t line = ((size_t)(s + (size_t)r * m->box0 * 8) >> 7) & 7;
+            const size_t line = ((size_t)(s + (size_t)r * m->box0 * 8) >> 7) & (m->swz == 2 ? 3 : 7);
             const int chunk = e >> 1;
             const int pch = m->swz ? (chunk ^ (int)line) : chunk;
             const double v = *(const double *)(s + (size_t)r * m->box0 * 8 + (size_t)pch * 16 + (e & 1) * 8);
@@ -202,7 +212,7 @@ static inline void nsb_tma_3d_g2s(void *dst, const nsb_tmap *m, int c0, int c1, 
             double v = 0.0;
             if (i2 >= 0 && i2 < m->dim2 && i1 >= 0 && i1 < m->dim1 && i0 >= 0 && i0 < m->dim0)
                 v = *(const double *)((const char *)m->base + i2 * m->stride2 + i1 * m->stride1 + i0 * 8);
-            const size_t line = ((size_t)(d + (size_t)r * m->box0 * 8) >> 7) & 7;
+            const size_t line = ((size_t)(d + (size_t)r * m->box0 * 8) >> 7) & (m->swz == 2 ? 3 : 7);
             const int chunk = e >> 1;
             const int pch = m->swz ? (chunk ^ (int)line) : chunk;
             *(double *)(d + (size_t)r * m->box0 * 8 + (size_t)pch * 16 + (e & 1) * 8) = v;

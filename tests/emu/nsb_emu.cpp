@@ -31,6 +31,13 @@ void barrier() {
     while (g.block_gen == gen) yield();
 }
 
+/* bar.sync id, nthreads: every participant names the same count; exited threads do not take part */
+void named_barrier(int id, int nthreads) {
+    const unsigned gen = g.named_gen[id];
+    if (++g.named_arrived[id] == nthreads) { g.named_arrived[id] = 0; g.named_gen[id]++; return; }
+    while (g.named_gen[id] == gen) yield();
+}
+
 void warp_barrier() {
     const int w = g.cur->warp;
     const unsigned gen = g.warp_gen[w];
@@ -89,6 +96,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> body
                         }
                 g.live = (int)nthreads;
                 g.block_arrived = 0;
+                for (int k = 0; k < 16; ++k) { g.named_arrived[k] = 0; g.named_gen[k] = 0; }
                 unsigned guard = 0;
                 while (g.live > 0) {
                     for (unsigned k = 0; k < nthreads; ++k) {

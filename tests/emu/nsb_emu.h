@@ -63,11 +63,14 @@ struct State {
     std::vector<int> warp_live, warp_arrived;
     std::vector<unsigned> warp_gen;
     std::vector<double> warp_buf;
+    int named_arrived[16];
+    unsigned named_gen[16];
     uint32_t tmem[128][512]; /* tensor memory of the current CTA (nsb_platform.h: nsb_tmem_*) */
 };
 extern State g;
 void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> body);
 void barrier();
+void named_barrier(int id, int nthreads);
 void warp_barrier();
 void yield();
 double shfl(double v, int src_lane);
