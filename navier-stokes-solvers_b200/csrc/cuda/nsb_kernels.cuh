@@ -1004,9 +1004,14 @@ struct NsbTmaps {
 #define NSB_UNROLL(n) NSB_PRAGMA_(unroll n)
 #define NSB_A1024_COLS 4 /* granularity of the column partition; kernels take 4 or 8 columns per CTA */
 #define NSB_A1024_SMEM(COLS) (1024 * 16 + 1024 * (COLS) * 16 + 32 * 16 + 1024 * 8)
-#define NSB_A1024_SMEM_TMA (NSB_A1024_SMEM(8) + 8 * 8192 + 16 + 1024)
+#define NSB_A1024_SMEM_TMA (NSB_A1024_SMEM(8) + 8 * 8192 + 32 + 1024)
 /* two groups: 2 x 64 KB tiles | 16 KB FFT twiddles | 2 x (TB 512 B + KY 8 KB) | 8 x 8 KB transpose buffers | 2 mbarriers */
-#define NSB_A1024_SMEM_2G (2 * 1024 * 4 * 16 + 1024 * 16 + 2 * (32 * 16 + 1024 * 8) + 8 * 8192 + 16 + 1024)
+#define NSB_A1024_SMEM_2G (2 * 1024 * 4 * 16 + 1024 * 16 + 2 * (32 * 16 + 1024 * 8) + 8 * 8192 + 32 + 1024)
+/* 1 (default): the TMA variants (8 warps, one CTA per SM) compute the reciprocal 1/k^2 once per mode: the first
+ * inverse job also forms the input of the second and parks it in the lane's own tensor-memory columns */
+#ifndef NSB_ALPHA_PARK
+#define NSB_ALPHA_PARK 1
+#endif
 
 /* shared tile S[1024 rows][4 columns], 16-byte chunks XOR-swizzled so that row-wise
  * (cooperative, coalesced) and column-wise (per-warp FFT) accesses are both conflict free */
@@ -1086,9 +1091,18 @@ __global__ void __launch_bounds__(COLS * 32 * GROUPS, 8 / (COLS * GROUPS))
     nsb_mbar_t *tbar = reinterpret_cast<nsb_mbar_t *>(reinterpret_cast<double *>(TW + 1024 + GROUPS * 32) +
                                                       (size_t)GROUPS * 1024 + 8 * 1024) + gi; /* TMA only */
     const cd *Wre = FWD ? a.rk.Wst : a.Wsrc; /* state the inverse fields derive from */
+    constexpr bool PARK = TMA && INV && (NSB_ALPHA_PARK != 0);
+    constexpr bool PARKT = TMA && (NSB_ALPHA_PARK != 0); /* y twiddles ta * TB[m] of the lane in columns 128..255 */
     nsb_fill_tw1024(TW, g.TWY);
     if (TMA && gt == 0) nsb_mbar_init(tbar, 1);
-    if (GROUPS > 1) __syncthreads(); /* the shared twiddle table; from here on the groups only meet themselves */
+    unsigned tbase = 0u, tcol = 0u;
+    if (PARKT) {
+        /* 256 tensor-memory columns per warp (two warps share a lane quadrant); block barrier inside */
+        tbase = nsb_tmem_alloc_all(reinterpret_cast<unsigned *>(tbar - gi + 2));
+        tcol = nsb_tmem_warp_base(tbase, (int)(threadIdx.x >> 5), (int)(threadIdx.x >> 7) * 256);
+    } else if (GROUPS > 1) {
+        __syncthreads(); /* the shared twiddle table; from here on the groups only meet themselves */
+    }
     /*
      * PERSISTENT over tiles (round 2): tile t = (j2, column tile), j2 slowest, CTA b takes t = b, b + gridDim.x, ...
      * The 16 KB twiddle table is staged once per CTA, the ky / y-twiddle rows only when j2 changes, and the last
@@ -1119,6 +1133,20 @@ __global__ void __launch_bounds__(COLS * 32 * GROUPS, 8 / (COLS * GROUPS))
         /* y twiddle exp(-2 pi i j2 y1/ny), y1 = lane + 32 m, factored as ta * TB[m] (measured: a full
          * 1024-entry table in shared memory costs more in lost L1 than the extra complex multiply) */
         ta = __ldg(&g.WY[(size_t)j2 * lane]);
+        if (PARKT && g.Y2 > 1) {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                double tpk[8];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const cd w = cmul(ta, __ldg(&g.WY[(size_t)32 * j2 * (4 * h + u)]));
+                    tpk[2 * u] = w.x;
+                    tpk[2 * u + 1] = w.y;
+                }
+                nsb_tmem_st8(tcol + 128 + 16 * h, tpk);
+            }
+            nsb_tmem_wait_st();
+        }
         for (int k = gt; k < 1024; k += COLS * 32) KY[k] = __ldg(&g.kyK[(size_t)j2 * 1024 + k]);
         /* rows of this lane that survive the 2/3 mask, one bit per register index (same for every job) */
         keepmask = 0u;
@@ -1157,21 +1185,72 @@ __global__ void __launch_bounds__(COLS * 32 * GROUPS, 8 / (COLS * GROUPS))
     for (int job = FWD ? 0 : 1; job <= (INV ? 4 : 0); ++job) {
         if (active) {
             if (job == 0) {
+                if (PARKT && g.Y2 > 1) {
+                    NsbTmemRaw8 q[2];
+                    nsb_tmem_ld8_async(q[0], tcol + 128);
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) {
+                        double tpk[8];
+                        nsb_tmem_wait_ld8(tpk, q[h & 1]);
+                        if (h < 7) nsb_tmem_ld8_async(q[(h + 1) & 1], tcol + 128 + 16 * (h + 1));
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int m = 4 * h + u;
+                            const cd v = cmul(S[nsb_sidx<COLS>(lane + 32 * m, warp)], cmk(tpk[2 * u], tpk[2 * u + 1]));
+                            x[m] = cmk(v.x, -v.y);
+                        }
+                    }
+                } else {
 #pragma unroll
                 for (int m = 0; m < 32; ++m) {
                     cd v = S[nsb_sidx<COLS>(lane + 32 * m, warp)];
                     if (g.Y2 > 1) v = cmul(v, cmul(ta, TB[m]));
                     x[m] = cmk(v.x, -v.y); /* forward = conj o inverse o conj */
                 }
+                }
                 __syncwarp(); /* every lane holds its values before the transpose reuses the slots */
             } else {
                 const int f = job - 1;
                 /* all 32 state loads in flight at once (unconditional: K layout covers every row);
                  * for jobs 2-4 they were issued before the previous job's store phase */
-                if (!prefetched) {
+                if (!prefetched && !(PARK && f == 1)) {
 #pragma unroll
                     for (int m = 0; m < 32; ++m) x[m] = Wre[kbase + lane + 32 * m];
                 }
+                if (PARK && f == 0) {
+                    /* -i (kx/k^2) w now, -i (ky/k^2) w parked for the next job: one reciprocal serves both */
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) {
+                        double tpk[8];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int m = 4 * h + u;
+                            const double kyv = KY[lane + 32 * m];
+                            const double k2 = __dadd_rn(kx2, __dmul_rn(kyv, kyv));
+                            double k0 = 0.0, k1 = 0.0;
+                            if (k2 > 1e-12) {
+                                const double r = nsb_drcp(k2);
+                                k0 = -(kxv * r);
+                                k1 = -(kyv * r);
+                            }
+                            if (!((keepmask >> m) & 1u)) k0 = k1 = 0.0;
+                            const cd y = nsb_ik(k1, x[m]);
+                            tpk[2 * u] = y.x;
+                            tpk[2 * u + 1] = y.y;
+                            x[m] = nsb_ik(k0, x[m]);
+                        }
+                        nsb_tmem_st8(tcol + 16 * h, tpk);
+                    }
+                    nsb_tmem_wait_st();
+                } else if (PARK && f == 1) {
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) {
+                        double tpk[8];
+                        nsb_tmem_ld8(tpk, tcol + 16 * h);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) x[4 * h + u] = cmk(tpk[2 * u], tpk[2 * u + 1]);
+                    }
+                } else
 #pragma unroll
                 for (int m = 0; m < 32; ++m) {
                     const int j1 = lane + 32 * m;
@@ -1311,15 +1390,31 @@ __global__ void __launch_bounds__(COLS * 32 * GROUPS, 8 / (COLS * GROUPS))
             NSB_GSYNC();
         }
         if (active) {
+            if (PARKT && g.Y2 > 1) {
+                NsbTmemRaw8 q[2];
+                nsb_tmem_ld8_async(q[0], tcol + 128);
+#pragma unroll
+                for (int h = 0; h < 8; ++h) {
+                    double tpk[8];
+                    nsb_tmem_wait_ld8(tpk, q[h & 1]);
+                    if (h < 7) nsb_tmem_ld8_async(q[(h + 1) & 1], tcol + 128 + 16 * (h + 1));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int m = 4 * h + u;
+                        S[nsb_sidx<COLS>(lane + 32 * m, warp)] = cmulc(x[m], cmk(tpk[2 * u], tpk[2 * u + 1]));
+                    }
+                }
+            } else {
 #pragma unroll
             for (int m = 0; m < 32; ++m) {
                 cd v = x[m];
                 if (g.Y2 > 1) v = cmulc(v, cmul(ta, TB[m]));
                 S[nsb_sidx<COLS>(lane + 32 * m, warp)] = v;
             }
+            }
             /* registers are free until the next transform: fetch its input now so the
              * latency hides behind the barrier and the cooperative store of this tile */
-            if (job < 4) {
+            if (job < 4 && !(PARK && job == 1)) {
 #pragma unroll
                 for (int m = 0; m < 32; ++m) x[m] = Wre[kbase + lane + 32 * m];
                 prefetched = true;
@@ -1371,6 +1466,10 @@ __global__ void __launch_bounds__(COLS * 32 * GROUPS, 8 / (COLS * GROUPS))
     }
     } /* tile loop */
     if (TMA && INV && gt == 0) nsb_tma_store_wait_read(); /* shared memory must outlive the last store */
+    if (PARKT) {
+        __syncthreads();
+        nsb_tmem_free_all(tbase);
+    }
 #undef NSB_GSYNC
 }
 

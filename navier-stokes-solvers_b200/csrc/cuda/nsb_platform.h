@@ -289,6 +289,9 @@ static inline void nsb_tmem_st8(unsigned t, const double (&v)[8]) { nsb_tmem_stN
 static inline void nsb_tmem_ld8(double (&v)[8], unsigned t) { nsb_tmem_ldN<8>(v, t); }
 static inline void nsb_tmem_wait_st() {}
 static inline void nsb_tmem_wait_ld() {}
+struct NsbTmemRaw8 { double d[8]; };
+static inline void nsb_tmem_ld8_async(NsbTmemRaw8 &q, unsigned t) { nsb_tmem_ldN<8>(q.d, t); }
+static inline void nsb_tmem_wait_ld8(double (&v)[8], NsbTmemRaw8 &q) { memcpy(v, q.d, sizeof(q.d)); }
 #else
 /* one warp allocates all 512 columns (one CTA per SM by construction), every thread gets the base address */
 __device__ __forceinline__ unsigned nsb_tmem_alloc_all(unsigned *slot_smem) {
@@ -346,6 +349,26 @@ __device__ __forceinline__ void nsb_tmem_ld8(double (&v)[8], unsigned taddr) {
         : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7])
         : "r"(taddr)
         : "memory");
+}
+/* split form of nsb_tmem_ld8 so that the next load can be in flight while the previous values are used: the raw
+ * 32-bit registers must not be read before nsb_tmem_wait_ld8 (which carries them as in/out operands, so no use
+ * can move above it) has turned them into doubles */
+struct NsbTmemRaw8 { unsigned r[16]; };
+__device__ __forceinline__ void nsb_tmem_ld8_async(NsbTmemRaw8 &q, unsigned taddr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(q.r[0]), "=r"(q.r[1]), "=r"(q.r[2]), "=r"(q.r[3]), "=r"(q.r[4]), "=r"(q.r[5]), "=r"(q.r[6]), "=r"(q.r[7]),
+                   "=r"(q.r[8]), "=r"(q.r[9]), "=r"(q.r[10]), "=r"(q.r[11]), "=r"(q.r[12]), "=r"(q.r[13]), "=r"(q.r[14]), "=r"(q.r[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void nsb_tmem_wait_ld8(double (&v)[8], NsbTmemRaw8 &q) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(q.r[0]), "+r"(q.r[1]), "+r"(q.r[2]), "+r"(q.r[3]), "+r"(q.r[4]), "+r"(q.r[5]), "+r"(q.r[6]), "+r"(q.r[7]),
+                   "+r"(q.r[8]), "+r"(q.r[9]), "+r"(q.r[10]), "+r"(q.r[11]), "+r"(q.r[12]), "+r"(q.r[13]), "+r"(q.r[14]), "+r"(q.r[15])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __hiloint2double((int)q.r[2 * i + 1], (int)q.r[2 * i]);
 }
 __device__ __forceinline__ void nsb_tmem_st16(unsigned taddr, const double (&v)[16]) {
     asm volatile(
