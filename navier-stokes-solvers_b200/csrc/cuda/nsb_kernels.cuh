@@ -1012,6 +1012,9 @@ struct NsbTmaps {
 #ifndef NSB_ALPHA_PARK
 #define NSB_ALPHA_PARK 1
 #endif
+#ifndef NSB_ALPHA_UNPARK16
+#define NSB_ALPHA_UNPARK16 0
+#endif
 
 /* shared tile S[1024 rows][4 columns], 16-byte chunks XOR-swizzled so that row-wise
  * (cooperative, coalesced) and column-wise (per-warp FFT) accesses are both conflict free */
@@ -1210,45 +1213,100 @@ __global__ void __launch_bounds__(COLS * 32 * GROUPS, 8 / (COLS * GROUPS))
                 }
                 __syncwarp(); /* every lane holds its values before the transpose reuses the slots */
             } else {
-                const int f = job - 1;
+                /* PARK: field order 2, 3, 0, 1 -- the state W is parked in the lane's tensor-memory columns by the
+                 * first job and read back by the next two (no reload from global memory between jobs); the third
+                 * forms -i (kx/k^2) w and -i (ky/k^2) w from ONE reciprocal per mode and parks the latter, over W,
+                 * for the fourth. Same arithmetic per field as the plain order: bit-identical T. */
+                const int f = PARK ? ((job + 1) & 3) : job - 1;
                 /* all 32 state loads in flight at once (unconditional: K layout covers every row);
-                 * for jobs 2-4 they were issued before the previous job's store phase */
-                if (!prefetched && !(PARK && f == 1)) {
+                 * without PARK they were issued before the previous job's store phase for jobs 2-4 */
+                if (!prefetched && !(PARK && job > 1)) {
 #pragma unroll
                     for (int m = 0; m < 32; ++m) x[m] = Wre[kbase + lane + 32 * m];
                 }
-                if (PARK && f == 0) {
-                    /* -i (kx/k^2) w now, -i (ky/k^2) w parked for the next job: one reciprocal serves both */
+                if (PARK) {
+                    /* the parked 32 values back into x, four at a time, the next load in flight behind `use` */
+                    auto unpark = [&](auto use) {
+#if NSB_ALPHA_UNPARK16 == 2
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) {
-                        double tpk[8];
+                        for (int h = 0; h < 8; ++h) {
+                            double tpk[8];
+                            nsb_tmem_ld8(tpk, tcol + 16 * h);
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int m = 4 * h + u;
-                            const double kyv = KY[lane + 32 * m];
-                            const double k2 = __dadd_rn(kx2, __dmul_rn(kyv, kyv));
-                            double k0 = 0.0, k1 = 0.0;
-                            if (k2 > 1e-12) {
-                                const double r = nsb_drcp(k2);
-                                k0 = -(kxv * r);
-                                k1 = -(kyv * r);
-                            }
-                            if (!((keepmask >> m) & 1u)) k0 = k1 = 0.0;
-                            const cd y = nsb_ik(k1, x[m]);
-                            tpk[2 * u] = y.x;
-                            tpk[2 * u + 1] = y.y;
-                            x[m] = nsb_ik(k0, x[m]);
+                            for (int u = 0; u < 4; ++u) x[4 * h + u] = cmk(tpk[2 * u], tpk[2 * u + 1]);
+                            use(h);
                         }
-                        nsb_tmem_st8(tcol + 16 * h, tpk);
-                    }
-                    nsb_tmem_wait_st();
-                } else if (PARK && f == 1) {
+#elif NSB_ALPHA_UNPARK16
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) {
-                        double tpk[8];
-                        nsb_tmem_ld8(tpk, tcol + 16 * h);
+                        for (int h2 = 0; h2 < 4; ++h2) {
+                            double tpk[16];
+                            nsb_tmem_ld16(tpk, tcol + 32 * h2);
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) x[4 * h + u] = cmk(tpk[2 * u], tpk[2 * u + 1]);
+                            for (int u = 0; u < 8; ++u) x[8 * h2 + u] = cmk(tpk[2 * u], tpk[2 * u + 1]);
+                            use(2 * h2);
+                            use(2 * h2 + 1);
+                        }
+#else
+                        NsbTmemRaw8 q[2];
+                        nsb_tmem_ld8_async(q[0], tcol);
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) {
+                            double tpk[8];
+                            nsb_tmem_wait_ld8(tpk, q[h & 1]);
+                            if (h < 7) nsb_tmem_ld8_async(q[(h + 1) & 1], tcol + 16 * (h + 1));
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) x[4 * h + u] = cmk(tpk[2 * u], tpk[2 * u + 1]);
+                            use(h);
+                        }
+#endif
+                    };
+                    if (job == 1) {
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) {
+                            double tpk[8];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int m = 4 * h + u;
+                                tpk[2 * u] = x[m].x;
+                                tpk[2 * u + 1] = x[m].y;
+                                x[m] = nsb_ik(((keepmask >> m) & 1u) ? kxv : 0.0, x[m]);
+                            }
+                            nsb_tmem_st8(tcol + 16 * h, tpk);
+                        }
+                        nsb_tmem_wait_st();
+                    } else if (job == 2) {
+                        unpark([&](int h) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int m = 4 * h + u;
+                                x[m] = nsb_ik(((keepmask >> m) & 1u) ? KY[lane + 32 * m] : 0.0, x[m]);
+                            }
+                        });
+                    } else if (job == 3) {
+                        unpark([&](int h) {
+                            double tpk[8];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int m = 4 * h + u;
+                                const double kyv = KY[lane + 32 * m];
+                                const double k2 = __dadd_rn(kx2, __dmul_rn(kyv, kyv));
+                                double k0 = 0.0, k1 = 0.0;
+                                if (k2 > 1e-12) {
+                                    const double r = nsb_drcp(k2);
+                                    k0 = -(kxv * r);
+                                    k1 = -(kyv * r);
+                                }
+                                if (!((keepmask >> m) & 1u)) k0 = k1 = 0.0;
+                                const cd y = nsb_ik(k1, x[m]);
+                                tpk[2 * u] = y.x;
+                                tpk[2 * u + 1] = y.y;
+                                x[m] = nsb_ik(k0, x[m]);
+                            }
+                            nsb_tmem_st8(tcol + 16 * h, tpk);
+                        });
+                        nsb_tmem_wait_st();
+                    } else {
+                        unpark([](int) {}); /* parked ready-made by the third job */
                     }
                 } else
 #pragma unroll
@@ -1414,7 +1472,7 @@ __global__ void __launch_bounds__(COLS * 32 * GROUPS, 8 / (COLS * GROUPS))
             }
             /* registers are free until the next transform: fetch its input now so the
              * latency hides behind the barrier and the cooperative store of this tile */
-            if (job < 4 && !(PARK && job == 1)) {
+            if (job < 4 && !PARK) {
 #pragma unroll
                 for (int m = 0; m < 32; ++m) x[m] = Wre[kbase + lane + 32 * m];
                 prefetched = true;
@@ -1444,7 +1502,7 @@ __global__ void __launch_bounds__(COLS * 32 * GROUPS, 8 / (COLS * GROUPS))
                 for (int r0 = 0; r0 < 1024; r0 += a.tma_br) {
                     const int owner = r0 / a.tma_rl;
                     nsb_tma_3d_s2g(COLS == 4 ? &tm.m4[owner] : &tm.m[owner], S + (size_t)r0 * COLS, 2 * ic0, j2,
-                                   (job - 1) * a.tma_rl + (r0 - owner * a.tma_rl));
+                                   (PARK ? ((job + 1) & 3) : job - 1) * a.tma_rl + (r0 - owner * a.tma_rl));
                 }
                 nsb_tma_store_commit();
             }
