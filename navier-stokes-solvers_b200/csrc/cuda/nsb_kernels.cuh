@@ -1216,7 +1216,9 @@ __global__ void __launch_bounds__(COLS * 32 * GROUPS, 8 / (COLS * GROUPS))
                 /* PARK: field order 2, 3, 0, 1 -- the state W is parked in the lane's tensor-memory columns by the
                  * first job and read back by the next two (no reload from global memory between jobs); the third
                  * forms -i (kx/k^2) w and -i (ky/k^2) w from ONE reciprocal per mode and parks the latter, over W,
-                 * for the fourth. Same arithmetic per field as the plain order: bit-identical T. */
+                 * for the fourth. Same formulas per field as the plain order (the compiler contracts the parked twiddle
+                 * product into FMAs differently, so T agrees with the unparked variants to rounding, not bit for bit;
+                 * every device count runs this same code and stays bit-identical to the others). */
                 const int f = PARK ? ((job + 1) & 3) : job - 1;
                 /* all 32 state loads in flight at once (unconditional: K layout covers every row);
                  * without PARK they were issued before the previous job's store phase for jobs 2-4 */
